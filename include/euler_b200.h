@@ -1,0 +1,219 @@
+/*
+ * euler_b200.h -- C ABI of the B200-native explicit saturation transport.
+ *
+ * This is the boundary a host simulator binds to in place of opm-porsol's
+ *     Opm::EulerUpstream<GridInterface, ReservoirProperties, BoundaryConditions>
+ * (reference: opm/porsol/euler/EulerUpstream.hpp:51-146).  The reference has no FFI: its
+ * "plugin API" is that class template, selected by SimulatorTraits.hpp:89-101 and called from
+ * SimulatorBase.hpp:213 / examples/SimulatorTester.hpp:83-85.  The header-only C++ mirror of
+ * that template (opm-porsol_b200/host/opm/porsol/euler/EulerUpstream.hpp) flattens whatever
+ * grid / property / boundary-condition objects it is given and forwards to the entry points
+ * below; INTEGRATION.md shows the two-line change a maintainer makes.
+ *
+ * Conventions
+ *   - plain C types, caller-owned host buffers, no exceptions across the boundary;
+ *   - every call returns EU_OK (0) or an error code; eu_last_error() gives the text;
+ *   - all floating point data is IEEE double, all indices are 32-bit int;
+ *   - cells are numbered in the reference's cell iteration order (== c->index(), as for
+ *     CpGrid, GridInterfaceEuler.hpp:70-80); the half-faces of a cell are stored in the order
+ *     `for (f = c->facebegin(); f != c->faceend(); ++f)`, i.e. "the reference's face order";
+ *     a half-face index is the running count in that double loop and equals the index of
+ *     FlowSolution::outflux(int hf) (IncompFlowSolverHybrid.hpp:430-433);
+ *   - there is NO CPU fallback: every entry point that computes needs a CUDA device and the
+ *     compiled sm_100a kernels, and fails with EU_ERR_CUDA otherwise.
+ */
+#ifndef EULER_B200_H
+#define EULER_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EU_ABI_VERSION 1
+
+typedef struct eu_solver* eu_handle;
+
+enum {
+    EU_OK = 0,
+    EU_ERR_ARG = 1,            /* bad argument / call order */
+    EU_ERR_CUDA = 2,           /* CUDA runtime failure or no device */
+    EU_ERR_SAT_RANGE = 3,      /* "Saturation out of range in EulerUpstream" after 10 retries
+                                  (EulerUpstream_impl.hpp:203-212,344-346) */
+    EU_ERR_CFL_ZERO = 4,       /* "Cfl computation gave dt = 0.0" (CflCalculator.hpp:75-77) */
+    EU_ERR_UNSUPPORTED = 5,
+    EU_ERR_COMM = 6
+};
+
+/* half-face kinds */
+enum { EU_HF_INTERIOR = 0, EU_HF_DIRICHLET = 1, EU_HF_PERIODIC = 2 };
+
+/* mobility kinds: ReservoirPropertyCapillary<3> (ScalarMobility) or
+ * ReservoirPropertyCapillaryAnisotropicRelperm<3> (diagonal TensorMobility<3>) */
+enum { EU_MOB_SCALAR = 0, EU_MOB_DIAGONAL = 1 };
+
+/* arithmetic modes */
+enum {
+    EU_MODE_AUTO = 0,    /* fast where implemented (scalar mobility), strict otherwise */
+    EU_MODE_STRICT = 1,  /* reference operation order, no FMA contraction: bit-identical to the reference */
+    EU_MODE_FAST = 2     /* static per-face quantities pre-contracted to scalars, FMA allowed:
+                            |dS| error ~1e-16 per substep (gate: 1e-12), identical step counts */
+};
+
+typedef struct eu_config {
+    int abi_version;       /* EU_ABI_VERSION */
+    int device;            /* CUDA device ordinal of this process */
+    int mode;              /* EU_MODE_* */
+    /* z-slab / index-range decomposition: this process owns global cells [own_begin, own_end).
+       world_size == 1: own_begin = 0, own_end = number of cells. */
+    int rank;
+    int world_size;
+    int own_begin;
+    int own_end;
+} eu_config;
+
+/* The 11 scalars of EulerUpstream (EulerUpstream_impl.hpp:59-73; keys read at :95-108). */
+typedef struct eu_params {
+    double courant_number;       /* 0.5 */
+    int method_viscous;          /* true */
+    int method_gravity;          /* true */
+    int method_capillary;        /* true */
+    int use_cfl_viscous;         /* true */
+    int use_cfl_gravity;         /* true */
+    int use_cfl_capillary;       /* true */
+    int minimum_small_steps;     /* 1 */
+    int maximum_small_steps;     /* 10000 */
+    int check_sat;               /* true */
+    int clamp_sat;               /* false */
+} eu_params;
+
+/* One chunk of consecutive cells [first_cell, first_cell + n_cells) with their half-faces,
+ * replacing the walk over GridInterfaceEuler (GridInterfaceEuler.hpp:126-216,335-363) and the
+ * per-cell property accessors (ReservoirPropertyCommon.hpp:130,150; cell_to_rock_).
+ * A rank of a decomposed run appends its own cells and every remote cell its faces touch
+ * (ghost cells), in ascending global cell order. */
+typedef struct eu_grid_chunk {
+    int first_cell;
+    int n_cells;
+    const int* hf_count;          /* n_cells: number of half-faces of each cell */
+    /* per half-face, n_hf = sum(hf_count) */
+    const int* hf_neighbour;      /* neighbour cell (global), -1 on the boundary
+                                     (Face::neighbourCellIndex(), GridInterfaceEuler.hpp:192-199) */
+    const double* hf_area;        /* Face::area() */
+    const double* hf_normal;      /* 3*n_hf, Face::normal() (unit outer normal) */
+    const double* hf_centroid;    /* 3*n_hf, Face::centroid() */
+    /* boundary half-faces of this chunk (satCond(face), BoundaryConditions.hpp:420-425) */
+    int n_bnd;
+    const int* bnd_hf;            /* chunk-relative half-face index, ascending */
+    const int* bnd_kind;          /* EU_HF_DIRICHLET / EU_HF_PERIODIC */
+    const double* bnd_sat;        /* SatBC::saturation() for Dirichlet faces */
+    const int* bnd_partner_cell;  /* periodic: cell of bid_to_face_[getPeriodicPartner(bid)]
+                                     (EulerUpstreamResidual_impl.hpp:118-120) */
+    const int* bnd_partner_face;  /* periodic: localIndex() of that partner face */
+    /* per cell */
+    const double* cell_volume;    /* Cell::volume() */
+    const double* cell_centroid;  /* 3*n_cells, Cell::centroid() */
+    const double* porosity;       /* rp.porosity(c) */
+    const double* permeability;   /* 9*n_cells row-major, rp.permeability(c) */
+    const int* rock_id;           /* cell_to_rock_[c]; may be NULL when there are no rock tables */
+} eu_grid_chunk;
+
+/* Fluid and rock description (ReservoirPropertyCommon.hpp:232-248, RockJfunc.hpp:220-228,
+ * RockAnisotropicRelperm.hpp:154-159). */
+typedef struct eu_fluid {
+    int mobility_kind;           /* EU_MOB_* */
+    double viscosity[2];
+    double density[2];
+    double cfl_factor[3];        /* rp.cflFactor(), cflFactorGravity(), cflFactorCapillary() */
+    int use_jfunction_scaling;   /* RockJfunc::use_jfunction_scaling_ (scalar mobility only) */
+    double sigma_cos_theta;      /* RockJfunc::sigma_cos_theta_ */
+    int n_rocks;                 /* 0: no rock tables -> quadratic relperm, pc = 1e5(1-S) */
+    const int* table_offset;     /* n_rocks+1 offsets into the concatenated node arrays */
+    const double* table_s;       /* saturation nodes */
+    /* EU_MOB_SCALAR:   columns {krw, kro, J}
+       EU_MOB_DIAGONAL: columns {pc, krxx_w, kryy_w, krzz_w, krxx_o, kryy_o, krzz_o} */
+    const double* table_cols[7];
+} eu_fluid;
+
+/* Per-call report of eu_transport_solve. */
+typedef struct eu_report {
+    int status;                  /* EU_OK, EU_ERR_SAT_RANGE or EU_ERR_CFL_ZERO */
+    int nsteps;                  /* nr_transport_steps of the last attempt */
+    int attempts;                /* 1 + number of retries ("repeats") */
+    long long substeps_executed; /* substeps launched over all attempts */
+    int bad_cell;                /* first offending cell of the failing substep, or -1 */
+    double bad_value;            /* its saturation */
+    double cfl_dt[3];            /* viscous, gravity, capillary CFL times (1e99 when unused) */
+    double dt;                   /* dt_transport of the last attempt */
+    double device_ms;            /* CUDA-event time of the substep loop of the last attempt */
+    int kernel_launches;         /* kernels launched by this call */
+} eu_report;
+
+/* ---- life cycle ------------------------------------------------------------------------ */
+int eu_create(const eu_config* cfg, eu_handle* out);
+void eu_destroy(eu_handle h);
+const char* eu_last_error(eu_handle h);     /* h may be NULL: error of the last failed eu_create */
+int eu_abi_version(void);
+
+/* EulerUpstream::init(param) (EulerUpstream_impl.hpp:95-108) */
+int eu_set_params(eu_handle h, const eu_params* p);
+void eu_default_params(eu_params* p);       /* EulerUpstream::EulerUpstream() (:59-73) */
+
+/* ---- EulerUpstream::initObj(grid, resprop, boundary) (EulerUpstream_impl.hpp:119-127,
+ *      EulerUpstreamResidual_impl.hpp:391-432) ------------------------------------------- */
+/* n_local_cells / n_local_halffaces: exact totals of what eu_grid_append will deliver to this
+ * rank (own + ghost); device storage is sized from them. */
+int eu_grid_begin(eu_handle h, int n_cells_global, int n_local_cells, long long n_local_halffaces);
+int eu_grid_append(eu_handle h, const eu_grid_chunk* chunk);
+int eu_set_fluid(eu_handle h, const eu_fluid* fluid);
+int eu_grid_end(eu_handle h);               /* builds the device structures */
+
+/* number of local cells / half-faces held by this rank, in upload order (own + ghost) */
+int eu_local_cells(eu_handle h);
+long long eu_local_halffaces(eu_handle h);
+
+/* ---- EulerUpstream::transportSolve (EulerUpstream_impl.hpp:151-218) -------------------
+ * saturation:  local cells (in/out; ghost entries are inputs only)
+ * hf_flux:     pressure_sol.outflux(f) for every local half-face, upload order
+ * sources:     injection_rates as (cell, rate) pairs with ascending global cell index
+ * Host buffers; the copies to and from the device are part of the call. */
+int eu_transport_solve(eu_handle h, double* saturation, double time, const double gravity[3],
+                       const double* hf_flux, int n_src, const int* src_cell, const double* src_rate,
+                       eu_report* report);
+
+/* ---- device-resident variant: state stays in HBM between calls ------------------------- */
+int eu_upload_state(eu_handle h, const double* saturation, const double* hf_flux);
+int eu_upload_saturation(eu_handle h, const double* saturation);
+int eu_download_saturation(eu_handle h, double* saturation);
+int eu_transport_solve_resident(eu_handle h, double time, const double gravity[3],
+                                int n_src, const int* src_cell, const double* src_rate, eu_report* report);
+
+/* ---- pieces exposed for per-substep parity tests --------------------------------------
+ * eu_cfl_times: CflCalculator.hpp:54-176 on the resident state (always all three terms).
+ * eu_small_step: EulerUpstream::smallTimeStep (:355-385) once, on the resident state;
+ *                residual_out (local own cells) may be NULL. */
+int eu_cfl_times(eu_handle h, const double gravity[3], double out[3]);
+int eu_small_step(eu_handle h, double dt, const double gravity[3],
+                  int n_src, const int* src_cell, const double* src_rate,
+                  double* residual_out, int* bad_cell, double* bad_value);
+
+/* ---- multi-GPU plumbing (one process per GPU; see DESIGN.md "Multi-GPU") ----------------
+ * Ghost saturations travel as peer-to-peer stores over NVLink into buffers exported with CUDA
+ * IPC.  The host application only has to all-gather two opaque blobs between the ranks. */
+int eu_comm_blob_size(eu_handle h);                         /* bytes of this rank's blob */
+int eu_comm_export(eu_handle h, void* blob);                /* fill this rank's blob */
+int eu_comm_connect(eu_handle h, const void* all_blobs);    /* world_size blobs, rank order */
+/* host-side reductions the caller performs between ranks (min over ranks of each entry /
+ * max over ranks): installed as callbacks so the library stays free of MPI/NCCL. */
+typedef void (*eu_allreduce_fn)(void* user, double* values, int n, int op /*0 = min, 1 = max*/);
+int eu_comm_set_allreduce(eu_handle h, eu_allreduce_fn fn, void* user);
+
+/* ---- host-side helper, no device needed: ReservoirPropertyCapillary<3>::computeCflFactors
+ *      (ReservoirPropertyCapillary_impl.hpp:190-281) for callers without the reference's
+ *      property class (bench, Python).  perm/poro/rock_id cover n_cells cells. */
+int eu_compute_cfl_factors(const eu_fluid* fluid, int n_cells, const double* porosity,
+                           const double* permeability, const int* rock_id, double out[3]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EULER_B200_H */

@@ -1,0 +1,933 @@
+// Host side of the C ABI (include/euler_b200.h).
+//
+// Mirrors, call by call, what opm-porsol's EulerUpstream does on the host:
+//   eu_set_params            EulerUpstream::init(param)            euler/EulerUpstream_impl.hpp:95-108
+//   eu_grid_* / eu_set_fluid EulerUpstream::initObj(g, r, b)       :119-127 (+ Residual_impl.hpp:391-432)
+//   eu_transport_solve       EulerUpstream::transportSolve         :151-218
+//       CFL terms            computeCflTime                        :263-331
+//       step count           :163-172, retry loop :181-213, range check :336-349
+// The arithmetic runs in the kernels of eu_setup.cu (STRICT, setup, CFL) and eu_fast.cu (FAST).
+#include "eu_internal.h"
+
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+namespace {
+
+std::string g_create_error;
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    cudaError_t alloc(size_t count)
+    {
+        release();
+        n = count;
+        if (count == 0) return cudaSuccess;
+        return cudaMalloc((void**)&p, count*sizeof(T));
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+struct Range { int first, count, local; };
+
+} // namespace
+
+struct eu_solver {
+    eu_config cfg;
+    eu_params par;
+    int mode;                 // resolved: EU_MODE_STRICT or EU_MODE_FAST
+    int n_sms;
+    cudaStream_t st;
+    std::string err;
+
+    // ---- upload bookkeeping
+    bool grid_open = false, grid_ready = false, fluid_set = false;
+    int n_global = 0, n_local_expected = 0, n_local = 0;
+    long long H_expected = 0, H = 0;
+    std::vector<Range> ranges;
+    std::vector<int> h_hf_offset;
+    std::vector<int> b_hf, b_kind, b_pcell, b_pface;
+    std::vector<double> b_sat;
+    bool any_rock_ids = false;
+    int own_lo = 0, own_hi = 0;
+
+    // ---- fat static
+    DevBuf<int> d_hf_offset, d_hf_nbr, d_rock, d_bnd_kind, d_bnd_phf, d_bnd_pcell, d_l2g;
+    DevBuf<double> d_hf_area, d_hf_normal, d_hf_centroid, d_cell_volume, d_cell_centroid, d_poro, d_perm, d_bnd_sat;
+    DevBuf<int> d_range_first, d_range_count, d_range_local;
+    // ---- fluid
+    eu_fluid fluid;
+    std::vector<int> h_tab_offset;
+    std::vector<double> h_tab_s, h_tab_cols[7];
+    DevBuf<int> d_tab_offset, d_bucket;
+    DevBuf<double> d_tab_s, d_tab_cols[7], d_lam[2], d_lam_slope[2], d_J, d_J_slope;
+    EuTablesDev tab;
+    // ---- derived
+    DevBuf<int> d_owner_hf, d_fid_of_hf, d_slice_base, d_flags;
+    DevBuf<int2> d_strict_list, d_rec;
+    DevBuf<double> d_porevol, d_pcscale, d_q, d_G, d_T, d_nn;
+    DevBuf<unsigned char> d_rock8;
+    long long F = 0;
+    int n_slices = 0;
+    bool use_nn = false;
+    bool contracted = false;
+    double contracted_gravity[3] = { 0, 0, 0 };
+    int contracted_mg = -1;
+    // ---- state
+    DevBuf<double> d_S[2], d_pc[2], d_S_init, d_hf_flux, d_residual, d_block_min, d_scalars;
+    DevBuf<unsigned long long> d_fail_key;
+    DevBuf<int> d_src_cell;
+    DevBuf<double> d_src_rate;
+    int cur = 0;
+    bool state_ready = false;
+    // cached CFL terms
+    bool cfl_cap_valid = false, cfl_grav_valid = false;
+    double cfl_cap = 1e100, cfl_grav = 1e100, cfl_grav_gravity[3] = { 0, 0, 0 };
+    cudaEvent_t ev0, ev1;
+    // comm
+    eu_allreduce_fn allreduce = nullptr;
+    void* allreduce_user = nullptr;
+
+    EuGridDev grid() const
+    {
+        EuGridDev g;
+        g.n_local = n_local; g.own_lo = own_lo; g.own_hi = own_hi;
+        g.cell_global0 = ranges.size() == 1 ? ranges[0].first : -1;
+        g.H = H;
+        g.hf_offset = d_hf_offset.p; g.hf_nbr = d_hf_nbr.p; g.hf_area = d_hf_area.p;
+        g.hf_normal = d_hf_normal.p; g.hf_centroid = d_hf_centroid.p;
+        g.cell_volume = d_cell_volume.p; g.cell_centroid = d_cell_centroid.p;
+        g.poro = d_poro.p; g.perm = d_perm.p; g.rock = d_rock.p;
+        g.bnd_kind = d_bnd_kind.p; g.bnd_sat = d_bnd_sat.p; g.bnd_partner_hf = d_bnd_phf.p;
+        g.bnd_partner_cell = d_bnd_pcell.p; g.local_to_global = d_l2g.p;
+        return g;
+    }
+    EuFastDev fast() const
+    {
+        EuFastDev f;
+        f.n_slices = n_slices; f.slice_base = d_slice_base.p; f.rec = d_rec.p;
+        f.q = d_q.p; f.G = d_G.p; f.T = d_T.p; f.nn = use_nn ? d_nn.p : nullptr;
+        f.porevol = d_porevol.p; f.pcscale = d_pcscale.p; f.rock8 = d_rock8.p; f.F = F;
+        return f;
+    }
+    int global_to_local(int gcell) const
+    {
+        for (const Range& r : ranges) {
+            if (gcell >= r.first && gcell < r.first + r.count) return r.local + (gcell - r.first);
+        }
+        return -1;
+    }
+    int local_to_global(int lcell) const
+    {
+        for (const Range& r : ranges) {
+            if (lcell >= r.local && lcell < r.local + r.count) return r.first + (lcell - r.local);
+        }
+        return -1;
+    }
+};
+
+namespace {
+
+int fail(eu_handle h, int code, const std::string& msg)
+{
+    if (h) h->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define EU_CUDA(h, call)                                                                       \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            return fail(h, EU_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+        }                                                                                      \
+    } while (0)
+
+template <class T>
+int upload(eu_handle h, DevBuf<T>& dst, size_t offset, const T* src, size_t count)
+{
+    if (count == 0) return EU_OK;
+    if (offset + count > dst.n) return fail(h, EU_ERR_ARG, "upload past the announced size");
+    EU_CUDA(h, cudaMemcpyAsync(dst.p + offset, src, count*sizeof(T), cudaMemcpyHostToDevice, h->st));
+    return EU_OK;
+}
+
+template <class T>
+int upload_vec(eu_handle h, DevBuf<T>& dst, const std::vector<T>& v)
+{
+    EU_CUDA(h, dst.alloc(v.size()));
+    if (v.empty()) return EU_OK;
+    EU_CUDA(h, cudaMemcpyAsync(dst.p, v.data(), v.size()*sizeof(T), cudaMemcpyHostToDevice, h->st));
+    EU_CUDA(h, cudaStreamSynchronize(h->st));
+    return EU_OK;
+}
+
+// opm-core tableIndex for a bucket edge (host twin of eu_strict_math.cuh / the oracle shim)
+int table_index_host(const double* x, int size, double v)
+{
+    int n = size - 1;
+    if (n < 2) return 0;
+    int jl = 0, ju = n;
+    const bool ascend = x[n] > x[0];
+    while (ju - jl > 1) {
+        int jm = (ju + jl)/2;
+        if ((v >= x[jm]) == ascend) jl = jm; else ju = jm;
+    }
+    return jl;
+}
+
+void set_tables_struct(eu_handle h)
+{
+    EuTablesDev& t = h->tab;
+    t.kind = h->fluid.mobility_kind;
+    t.n_rocks = h->fluid.n_rocks;
+    t.n_nodes_total = int(h->h_tab_s.size());
+    t.use_j = h->fluid.use_jfunction_scaling;
+    t.sigma_cos_theta = h->fluid.sigma_cos_theta;
+    t.visc[0] = h->fluid.viscosity[0]; t.visc[1] = h->fluid.viscosity[1];
+    t.delta_rho = h->fluid.density[0] - h->fluid.density[1];       // densityDifference()
+    t.offset = h->d_tab_offset.p; t.s = h->d_tab_s.p;
+    for (int k = 0; k < 7; ++k) t.cols[k] = h->d_tab_cols[k].p;
+    t.lam[0] = h->d_lam[0].p; t.lam[1] = h->d_lam[1].p;
+    t.lam_slope[0] = h->d_lam_slope[0].p; t.lam_slope[1] = h->d_lam_slope[1].p;
+    t.J = h->d_J.p; t.J_slope = h->d_J_slope.p; t.bucket = h->d_bucket.p;
+}
+
+int ensure_contracted(eu_handle h, const double gravity[3])
+{
+    if (h->mode != EU_MODE_FAST) return EU_OK;
+    const int mg = h->par.method_gravity ? 1 : 0;
+    if (h->contracted && h->contracted_mg == mg && std::memcmp(h->contracted_gravity, gravity, 3*sizeof(double)) == 0)
+        return EU_OK;
+    eu_launch_contract(h->grid(), h->tab, h->d_owner_hf.p, h->d_fid_of_hf.p, gravity, mg, h->d_G.p, h->d_T.p, h->d_nn.p,
+                       h->d_scalars.p + 8, h->st);
+    double maxdev = 0.0;
+    EU_CUDA(h, cudaMemcpyAsync(&maxdev, h->d_scalars.p + 8, sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    EU_CUDA(h, cudaStreamSynchronize(h->st));
+    EU_CUDA(h, cudaGetLastError());
+    h->use_nn = maxdev > 1e-13;     // non-unit normals: keep the n.n factor of the viscous term
+    h->contracted = true;
+    h->contracted_mg = mg;
+    std::memcpy(h->contracted_gravity, gravity, 3*sizeof(double));
+    return EU_OK;
+}
+
+int upload_sources(eu_handle h, int n_src, const int* src_cell, const double* src_rate, int* n_local_src)
+{
+    std::vector<int> lc;
+    std::vector<double> lr;
+    for (int i = 0; i < n_src; ++i) {
+        if (i > 0 && src_cell[i] <= src_cell[i - 1]) return fail(h, EU_ERR_ARG, "source cells must be strictly ascending");
+        const int l = h->global_to_local(src_cell[i]);
+        if (l >= h->own_lo && l < h->own_hi) { lc.push_back(l); lr.push_back(src_rate[i]); }
+    }
+    *n_local_src = int(lc.size());
+    if (lc.empty()) return EU_OK;
+    if (h->d_src_cell.n < lc.size()) {
+        EU_CUDA(h, h->d_src_cell.alloc(lc.size()));
+        EU_CUDA(h, h->d_src_rate.alloc(lc.size()));
+    }
+    EU_CUDA(h, cudaMemcpyAsync(h->d_src_cell.p, lc.data(), lc.size()*sizeof(int), cudaMemcpyHostToDevice, h->st));
+    EU_CUDA(h, cudaMemcpyAsync(h->d_src_rate.p, lr.data(), lr.size()*sizeof(double), cudaMemcpyHostToDevice, h->st));
+    EU_CUDA(h, cudaStreamSynchronize(h->st));   // lc/lr go out of scope
+    return EU_OK;
+}
+
+EuStepArgs step_args(eu_handle h, double dt, const double gravity[3], int n_src, int substep)
+{
+    EuStepArgs a;
+    a.dt = dt;
+    a.method_viscous = h->par.method_viscous; a.method_gravity = h->par.method_gravity;
+    a.method_capillary = h->par.method_capillary;
+    a.check_sat = h->par.check_sat; a.clamp_sat = h->par.clamp_sat;
+    a.substep = substep;
+    a.n_src = n_src; a.src_cell = h->d_src_cell.p; a.src_rate = h->d_src_rate.p;
+    a.S_in = h->d_S[h->cur].p; a.S_out = h->d_S[h->cur ^ 1].p;
+    a.pc_in = h->d_pc[h->cur].p; a.pc_out = h->d_pc[h->cur ^ 1].p;
+    a.residual_out = nullptr;
+    a.fail_key = h->d_fail_key.p;
+    a.gravity[0] = gravity[0]; a.gravity[1] = gravity[1]; a.gravity[2] = gravity[2];
+    return a;
+}
+
+// one substep on the resident state; returns the number of kernels launched
+int launch_substep(eu_handle h, const EuStepArgs& a)
+{
+    const EuGridDev g = h->grid();
+    if (h->mode == EU_MODE_FAST) {
+        const int slice_lo = h->own_lo/EU_SLICE;
+        const int slice_hi = (h->own_hi + EU_SLICE - 1)/EU_SLICE;
+        eu_launch_fast_step(g, h->tab, h->fast(), a, slice_lo, slice_hi, h->n_sms, h->st);
+        return 1;
+    }
+    int launches = 1;
+    if (a.method_capillary) {
+        eu_launch_strict_pc(g, h->tab, a.S_in, const_cast<double*>(a.pc_in), h->st);
+        ++launches;
+    }
+    EuStrictDev s;
+    s.list = h->d_strict_list.p;
+    s.porevol = h->d_porevol.p;
+    eu_launch_strict_step(g, h->tab, s, h->d_hf_flux.p, a, h->st);
+    return launches;
+}
+
+int compute_cfl(eu_handle h, const double gravity[3], bool want_v, bool want_g, bool want_c, double out[3],
+                int* zero_flag, int* launches)
+{
+    const EuGridDev g = h->grid();
+    out[0] = out[1] = out[2] = 1e99;
+    *zero_flag = 0;
+    // The velocity pass also compacts the half-face fluxes for the FAST kernel, so it always runs.
+    EU_CUDA(h, cudaMemsetAsync(h->d_flags.p, 0, 4*sizeof(int), h->st));
+    eu_launch_cfl_velocity_compact(g, h->fluid.cfl_factor[0], h->d_hf_flux.p, h->d_fid_of_hf.p,
+                                   h->mode == EU_MODE_FAST ? h->d_q.p : nullptr, h->d_block_min.p, h->d_flags.p,
+                                   h->d_scalars.p + 0, h->st);
+    *launches += 2;
+    const bool grav_cached = h->cfl_grav_valid && std::memcmp(h->cfl_grav_gravity, gravity, 3*sizeof(double)) == 0;
+    if (want_g && !grav_cached) {
+        eu_launch_cfl_gravity(g, h->tab, h->fluid.cfl_factor[1], gravity, h->d_block_min.p, h->d_scalars.p + 1, h->st);
+        *launches += 2;
+    }
+    if (want_c && !h->cfl_cap_valid) {
+        eu_launch_cfl_capillary(g, h->fluid.cfl_factor[2], h->d_block_min.p, h->d_scalars.p + 2, h->st);
+        *launches += 2;
+    }
+    double host[3];
+    int flags[4];
+    EU_CUDA(h, cudaMemcpyAsync(host, h->d_scalars.p, 3*sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    EU_CUDA(h, cudaMemcpyAsync(flags, h->d_flags.p, 4*sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    EU_CUDA(h, cudaStreamSynchronize(h->st));
+    EU_CUDA(h, cudaGetLastError());
+    if (want_g && !grav_cached) {
+        h->cfl_grav = host[1];
+        h->cfl_grav_valid = true;
+        std::memcpy(h->cfl_grav_gravity, gravity, 3*sizeof(double));
+    }
+    if (want_c && !h->cfl_cap_valid) { h->cfl_cap = host[2]; h->cfl_cap_valid = true; }
+    double vals[4] = { host[0], want_g ? h->cfl_grav : 1e100, want_c ? h->cfl_cap : 1e100, 0.0 };
+    if (h->cfg.world_size > 1) {
+        if (!h->allreduce) return fail(h, EU_ERR_COMM, "world_size > 1 needs eu_comm_set_allreduce");
+        h->allreduce(h->allreduce_user, vals, 3, 0);
+        double z = flags[0] ? 1.0 : 0.0;
+        h->allreduce(h->allreduce_user, &z, 1, 1);
+        flags[0] = z != 0.0;
+    }
+    if (want_v) out[0] = vals[0];
+    if (want_g) out[1] = vals[1];
+    if (want_c) out[2] = vals[2];
+    *zero_flag = flags[0];
+    return EU_OK;
+}
+
+} // namespace
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+extern "C" {
+
+int eu_abi_version(void) { return EU_ABI_VERSION; }
+
+void eu_default_params(eu_params* p)
+{
+    p->courant_number = 0.5;
+    p->method_viscous = p->method_gravity = p->method_capillary = 1;
+    p->use_cfl_viscous = p->use_cfl_gravity = p->use_cfl_capillary = 1;
+    p->minimum_small_steps = 1;
+    p->maximum_small_steps = 10000;
+    p->check_sat = 1;
+    p->clamp_sat = 0;
+}
+
+const char* eu_last_error(eu_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int eu_create(const eu_config* cfg, eu_handle* out)
+{
+    if (!cfg || !out) return fail(nullptr, EU_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (cfg->abi_version != EU_ABI_VERSION) return fail(nullptr, EU_ERR_ARG, "ABI version mismatch");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, EU_ERR_CUDA, std::string("no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, EU_ERR_ARG, "bad device ordinal");
+    e = cudaSetDevice(cfg->device);
+    if (e != cudaSuccess) return fail(nullptr, EU_ERR_CUDA, cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, cfg->device);
+    if (e != cudaSuccess) return fail(nullptr, EU_ERR_CUDA, cudaGetErrorString(e));
+    if (prop.major < 10)
+        return fail(nullptr, EU_ERR_CUDA, "device is not sm_100-class: the kernels are built for sm_100a only");
+    eu_solver* h = new eu_solver;
+    h->cfg = *cfg;
+    if (h->cfg.world_size < 1) h->cfg.world_size = 1;
+    eu_default_params(&h->par);
+    h->mode = EU_MODE_STRICT;
+    h->n_sms = prop.multiProcessorCount;
+    std::memset(&h->fluid, 0, sizeof(h->fluid));
+    std::memset(&h->tab, 0, sizeof(h->tab));
+    if (cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {
+        delete h;
+        return fail(nullptr, EU_ERR_CUDA, "stream/event creation failed");
+    }
+    *out = h;
+    return EU_OK;
+}
+
+void eu_destroy(eu_handle h)
+{
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    cudaStreamSynchronize(h->st);
+    cudaEventDestroy(h->ev0);
+    cudaEventDestroy(h->ev1);
+    cudaStreamDestroy(h->st);
+    delete h;
+}
+
+int eu_set_params(eu_handle h, const eu_params* p)
+{
+    if (!h || !p) return EU_ERR_ARG;
+    h->par = *p;
+    return EU_OK;
+}
+
+int eu_grid_begin(eu_handle h, int n_cells_global, int n_local_cells, long long n_local_halffaces)
+{
+    if (!h) return EU_ERR_ARG;
+    if (n_cells_global <= 0 || n_local_cells <= 0 || n_local_halffaces <= 0 || n_local_halffaces > INT_MAX)
+        return fail(h, EU_ERR_ARG, "bad grid sizes (half-faces per rank must fit 32-bit)");
+    EU_CUDA(h, cudaSetDevice(h->cfg.device));
+    h->grid_open = true; h->grid_ready = false; h->state_ready = false; h->contracted = false;
+    h->cfl_cap_valid = h->cfl_grav_valid = false;
+    h->n_global = n_cells_global; h->n_local_expected = n_local_cells; h->H_expected = n_local_halffaces;
+    h->n_local = 0; h->H = 0;
+    h->ranges.clear();
+    h->h_hf_offset.assign(1, 0);
+    h->h_hf_offset.reserve(size_t(n_local_cells) + 1);
+    h->b_hf.clear(); h->b_kind.clear(); h->b_pcell.clear(); h->b_pface.clear(); h->b_sat.clear();
+    h->any_rock_ids = false;
+    const size_t n = size_t(n_local_cells), H = size_t(n_local_halffaces);
+    EU_CUDA(h, h->d_hf_nbr.alloc(H));
+    EU_CUDA(h, h->d_hf_area.alloc(H));
+    EU_CUDA(h, h->d_hf_normal.alloc(3*H));
+    EU_CUDA(h, h->d_hf_centroid.alloc(3*H));
+    EU_CUDA(h, h->d_cell_volume.alloc(n));
+    EU_CUDA(h, h->d_cell_centroid.alloc(3*n));
+    EU_CUDA(h, h->d_poro.alloc(n));
+    EU_CUDA(h, h->d_perm.alloc(9*n));
+    EU_CUDA(h, h->d_rock.alloc(n));
+    EU_CUDA(h, cudaMemsetAsync(h->d_rock.p, 0, n*sizeof(int), h->st));
+    return EU_OK;
+}
+
+int eu_grid_append(eu_handle h, const eu_grid_chunk* c)
+{
+    if (!h || !c) return EU_ERR_ARG;
+    if (!h->grid_open) return fail(h, EU_ERR_ARG, "eu_grid_append before eu_grid_begin");
+    if (c->n_cells <= 0) return EU_OK;
+    EU_CUDA(h, cudaSetDevice(h->cfg.device));
+    if (!h->ranges.empty()) {
+        const Range& last = h->ranges.back();
+        if (c->first_cell < last.first + last.count) return fail(h, EU_ERR_ARG, "chunks must come in ascending cell order");
+    }
+    if (c->first_cell < 0 || c->first_cell + c->n_cells > h->n_global) return fail(h, EU_ERR_ARG, "chunk outside the grid");
+    if (h->n_local + c->n_cells > h->n_local_expected) return fail(h, EU_ERR_ARG, "more cells than announced");
+    long long nhf = 0;
+    for (int i = 0; i < c->n_cells; ++i) {
+        if (c->hf_count[i] < 0) return fail(h, EU_ERR_ARG, "negative half-face count");
+        nhf += c->hf_count[i];
+        h->h_hf_offset.push_back(int(h->H + nhf));
+    }
+    if (h->H + nhf > h->H_expected) return fail(h, EU_ERR_ARG, "more half-faces than announced");
+    if (!h->ranges.empty() && h->ranges.back().first + h->ranges.back().count == c->first_cell) {
+        h->ranges.back().count += c->n_cells;
+    } else {
+        Range r = { c->first_cell, c->n_cells, h->n_local };
+        h->ranges.push_back(r);
+    }
+    // neighbour array with the boundary half-faces tagged -2-(boundary index)
+    std::vector<int> nbr(c->hf_neighbour, c->hf_neighbour + nhf);
+    for (int i = 0; i < c->n_bnd; ++i) {
+        const int rel = c->bnd_hf[i];
+        if (rel < 0 || rel >= nhf) return fail(h, EU_ERR_ARG, "boundary half-face index out of range");
+        if (nbr[rel] >= 0) return fail(h, EU_ERR_ARG, "boundary condition given for an interior half-face");
+        const int kind = c->bnd_kind[i];
+        if (kind != EU_HF_DIRICHLET && kind != EU_HF_PERIODIC) return fail(h, EU_ERR_ARG, "bad boundary kind");
+        nbr[rel] = -2 - int(h->b_hf.size());
+        h->b_hf.push_back(int(h->H + rel));
+        h->b_kind.push_back(kind);
+        h->b_sat.push_back(c->bnd_sat ? c->bnd_sat[i] : 1.0);
+        h->b_pcell.push_back(kind == EU_HF_PERIODIC ? c->bnd_partner_cell[i] : -1);
+        h->b_pface.push_back(kind == EU_HF_PERIODIC ? c->bnd_partner_face[i] : -1);
+    }
+    for (long long k = 0; k < nhf; ++k) {
+        if (nbr[k] == -1) return fail(h, EU_ERR_ARG, "boundary half-face without a saturation boundary condition");
+    }
+    const size_t o = size_t(h->H), oc = size_t(h->n_local);
+    int rc;
+    if ((rc = upload(h, h->d_hf_nbr, o, nbr.data(), size_t(nhf)))) return rc;
+    EU_CUDA(h, cudaStreamSynchronize(h->st));      // nbr is a temporary
+    if ((rc = upload(h, h->d_hf_area, o, c->hf_area, size_t(nhf)))) return rc;
+    if ((rc = upload(h, h->d_hf_normal, 3*o, c->hf_normal, size_t(3*nhf)))) return rc;
+    if ((rc = upload(h, h->d_hf_centroid, 3*o, c->hf_centroid, size_t(3*nhf)))) return rc;
+    if ((rc = upload(h, h->d_cell_volume, oc, c->cell_volume, size_t(c->n_cells)))) return rc;
+    if ((rc = upload(h, h->d_cell_centroid, 3*oc, c->cell_centroid, size_t(3*c->n_cells)))) return rc;
+    if ((rc = upload(h, h->d_poro, oc, c->porosity, size_t(c->n_cells)))) return rc;
+    if ((rc = upload(h, h->d_perm, 9*oc, c->permeability, size_t(9*c->n_cells)))) return rc;
+    if (c->rock_id) {
+        h->any_rock_ids = true;
+        if ((rc = upload(h, h->d_rock, oc, c->rock_id, size_t(c->n_cells)))) return rc;
+    }
+    EU_CUDA(h, cudaStreamSynchronize(h->st));
+    h->H += nhf;
+    h->n_local += c->n_cells;
+    return EU_OK;
+}
+
+int eu_set_fluid(eu_handle h, const eu_fluid* f)
+{
+    if (!h || !f) return EU_ERR_ARG;
+    EU_CUDA(h, cudaSetDevice(h->cfg.device));
+    if (f->mobility_kind != EU_MOB_SCALAR && f->mobility_kind != EU_MOB_DIAGONAL) return fail(h, EU_ERR_ARG, "bad mobility kind");
+    if (f->n_rocks < 0 || f->n_rocks > EU_MAX_ROCKS) return fail(h, EU_ERR_UNSUPPORTED, "at most 16 rock types");
+    h->fluid = *f;
+    const int ncol = f->mobility_kind == EU_MOB_SCALAR ? 3 : 7;
+    h->h_tab_offset.assign(1, 0);
+    h->h_tab_s.clear();
+    for (int k = 0; k < 7; ++k) h->h_tab_cols[k].clear();
+    if (f->n_rocks > 0) {
+        h->h_tab_offset.assign(f->table_offset, f->table_offset + f->n_rocks + 1);
+        const int nn = h->h_tab_offset.back();
+        for (int r = 0; r < f->n_rocks; ++r) {
+            const int cnt = h->h_tab_offset[r + 1] - h->h_tab_offset[r];
+            if (cnt < 2) return fail(h, EU_ERR_ARG, "a rock table needs at least two nodes");
+            if (cnt > 250) return fail(h, EU_ERR_UNSUPPORTED, "at most 250 nodes per rock table");
+        }
+        h->h_tab_s.assign(f->table_s, f->table_s + nn);
+        for (int k = 0; k < ncol; ++k) h->h_tab_cols[k].assign(f->table_cols[k], f->table_cols[k] + nn);
+    }
+    int rc;
+    if ((rc = upload_vec(h, h->d_tab_offset, h->h_tab_offset))) return rc;
+    if ((rc = upload_vec(h, h->d_tab_s, h->h_tab_s))) return rc;
+    for (int k = 0; k < 7; ++k) if ((rc = upload_vec(h, h->d_tab_cols[k], h->h_tab_cols[k]))) return rc;
+    // FAST tables (scalar mobility): mobility = kr/viscosity at the nodes, slope per interval
+    if (f->mobility_kind == EU_MOB_SCALAR && f->n_rocks > 0) {
+        const int nn = int(h->h_tab_s.size());
+        std::vector<double> lam[2], sl[2], J(nn), Js(nn, 0.0);
+        std::vector<int> bucket(size_t(f->n_rocks)*EU_BUCKETS, 0);
+        for (int p = 0; p < 2; ++p) { lam[p].resize(nn); sl[p].assign(nn, 0.0); }
+        for (int i = 0; i < nn; ++i) {
+            lam[0][i] = h->h_tab_cols[0][i]/f->viscosity[0];
+            lam[1][i] = h->h_tab_cols[1][i]/f->viscosity[1];
+            J[i] = h->h_tab_cols[2][i];
+        }
+        for (int r = 0; r < f->n_rocks; ++r) {
+            const int b = h->h_tab_offset[r], e = h->h_tab_offset[r + 1];
+            for (int i = b; i + 1 < e; ++i) {
+                const double dx = h->h_tab_s[i + 1] - h->h_tab_s[i];
+                sl[0][i] = (lam[0][i + 1] - lam[0][i])/dx;
+                sl[1][i] = (lam[1][i + 1] - lam[1][i])/dx;
+                Js[i] = (J[i + 1] - J[i])/dx;
+            }
+            for (int k = 1; k < EU_BUCKETS; ++k) {
+                bucket[size_t(r)*EU_BUCKETS + k] = table_index_host(&h->h_tab_s[b], e - b, double(k)/EU_BUCKETS);
+            }
+        }
+        for (int p = 0; p < 2; ++p) {
+            if ((rc = upload_vec(h, h->d_lam[p], lam[p]))) return rc;
+            if ((rc = upload_vec(h, h->d_lam_slope[p], sl[p]))) return rc;
+        }
+        if ((rc = upload_vec(h, h->d_J, J))) return rc;
+        if ((rc = upload_vec(h, h->d_J_slope, Js))) return rc;
+        if ((rc = upload_vec(h, h->d_bucket, bucket))) return rc;
+    }
+    set_tables_struct(h);
+    h->fluid_set = true;
+    h->contracted = false;
+    h->cfl_cap_valid = h->cfl_grav_valid = false;
+    if (h->cfg.mode == EU_MODE_STRICT) h->mode = EU_MODE_STRICT;
+    else if (f->mobility_kind == EU_MOB_SCALAR) h->mode = EU_MODE_FAST;
+    else if (h->cfg.mode == EU_MODE_FAST) return fail(h, EU_ERR_UNSUPPORTED, "FAST mode implements scalar mobility only");
+    else h->mode = EU_MODE_STRICT;
+    return EU_OK;
+}
+
+int eu_grid_end(eu_handle h)
+{
+    if (!h) return EU_ERR_ARG;
+    if (!h->grid_open) return fail(h, EU_ERR_ARG, "eu_grid_end before eu_grid_begin");
+    if (!h->fluid_set) return fail(h, EU_ERR_ARG, "eu_set_fluid must precede eu_grid_end");
+    if (h->n_local != h->n_local_expected || h->H != h->H_expected) return fail(h, EU_ERR_ARG, "fewer cells/half-faces than announced");
+    if (h->fluid.n_rocks > 1 && !h->any_rock_ids) return fail(h, EU_ERR_ARG, "several rocks but no rock ids");
+    EU_CUDA(h, cudaSetDevice(h->cfg.device));
+    int rc;
+    // own range in local numbering
+    {
+        const int ob = h->cfg.world_size > 1 ? h->cfg.own_begin : 0;
+        const int oe = h->cfg.world_size > 1 ? h->cfg.own_end : h->n_global;
+        h->own_lo = h->global_to_local(ob);
+        const int last = h->global_to_local(oe - 1);
+        if (h->own_lo < 0 || last < 0 || last - h->own_lo != oe - 1 - ob) return fail(h, EU_ERR_ARG, "own cell range not fully uploaded");
+        h->own_hi = last + 1;
+    }
+    if ((rc = upload_vec(h, h->d_hf_offset, h->h_hf_offset))) return rc;
+    {
+        std::vector<int> rf, rcn, rl, l2g(size_t(h->n_local));
+        for (const Range& r : h->ranges) {
+            rf.push_back(r.first); rcn.push_back(r.count); rl.push_back(r.local);
+            for (int i = 0; i < r.count; ++i) l2g[size_t(r.local) + i] = r.first + i;
+        }
+        if ((rc = upload_vec(h, h->d_range_first, rf))) return rc;
+        if ((rc = upload_vec(h, h->d_range_count, rcn))) return rc;
+        if ((rc = upload_vec(h, h->d_range_local, rl))) return rc;
+        if ((rc = upload_vec(h, h->d_l2g, l2g))) return rc;
+        eu_launch_translate_nbr(h->d_hf_nbr.p, h->H, h->d_range_first.p, h->d_range_count.p, h->d_range_local.p, int(rf.size()), h->st);
+    }
+    // boundary tables; periodic partners -> local cell / half-face
+    {
+        const size_t nb = h->b_hf.size();
+        std::vector<int> phf(std::max<size_t>(nb, 1), -1), pcl(std::max<size_t>(nb, 1), -1), kind(std::max<size_t>(nb, 1), 0);
+        std::vector<double> sat(std::max<size_t>(nb, 1), 0.0);
+        for (size_t i = 0; i < nb; ++i) {
+            kind[i] = h->b_kind[i];
+            sat[i] = h->b_sat[i];
+            if (h->b_kind[i] == EU_HF_PERIODIC) {
+                const int l = h->global_to_local(h->b_pcell[i]);
+                if (l >= 0) {
+                    const int cnt = h->h_hf_offset[l + 1] - h->h_hf_offset[l];
+                    if (h->b_pface[i] < 0 || h->b_pface[i] >= cnt) return fail(h, EU_ERR_ARG, "periodic partner face out of range");
+                    pcl[i] = l;
+                    phf[i] = h->h_hf_offset[l] + h->b_pface[i];
+                }
+            }
+        }
+        if ((rc = upload_vec(h, h->d_bnd_kind, kind))) return rc;
+        if ((rc = upload_vec(h, h->d_bnd_sat, sat))) return rc;
+        if ((rc = upload_vec(h, h->d_bnd_phf, phf))) return rc;
+        if ((rc = upload_vec(h, h->d_bnd_pcell, pcl))) return rc;
+    }
+    const size_t n = size_t(h->n_local), H = size_t(h->H);
+    EU_CUDA(h, h->d_flags.alloc(4));
+    EU_CUDA(h, h->d_scalars.alloc(16));
+    EU_CUDA(h, cudaMemsetAsync(h->d_flags.p, 0, 4*sizeof(int), h->st));
+    EU_CUDA(h, h->d_owner_hf.alloc(H));
+    EU_CUDA(h, h->d_porevol.alloc(n));
+    const EuGridDev g = h->grid();
+    eu_launch_owner(g, h->d_owner_hf.p, h->d_flags.p, h->st);
+    eu_launch_porevol(g, h->d_porevol.p, h->st);
+    int flags[4] = { 0, 0, 0, 0 };
+    EU_CUDA(h, cudaMemcpyAsync(flags, h->d_flags.p, sizeof(flags), cudaMemcpyDeviceToHost, h->st));
+    EU_CUDA(h, cudaStreamSynchronize(h->st));
+    EU_CUDA(h, cudaGetLastError());
+    if (flags[0] == 1) return fail(h, EU_ERR_ARG, "connectivity is not symmetric (half-face without a matching half-face in the neighbour)");
+    if (flags[0] == 2) return fail(h, EU_ERR_ARG, "periodic partner cell of an own cell was not uploaded");
+    if (flags[0] == 3) return fail(h, EU_ERR_ARG, "neighbour (ghost) cell of an own cell was not uploaded");
+
+    EU_CUDA(h, h->d_fid_of_hf.alloc(H));
+    if (h->mode == EU_MODE_STRICT) {
+        EU_CUDA(h, h->d_strict_list.alloc(H));
+        eu_launch_strict_list(g, h->d_owner_hf.p, h->d_strict_list.p, h->st);
+        EU_CUDA(h, cudaMemsetAsync(h->d_fid_of_hf.p, 0xff, H*sizeof(int), h->st));
+    } else {
+        h->n_slices = (h->n_local + EU_SLICE - 1)/EU_SLICE;
+        DevBuf<int> d_width, d_nown, d_fid_base;
+        EU_CUDA(h, d_width.alloc(size_t(h->n_slices)));
+        EU_CUDA(h, d_nown.alloc(size_t(h->n_slices)));
+        eu_launch_slice_count(g, h->d_owner_hf.p, d_width.p, d_nown.p, h->st);
+        std::vector<int> width(size_t(h->n_slices)), nown(size_t(h->n_slices));
+        EU_CUDA(h, cudaMemcpyAsync(width.data(), d_width.p, width.size()*sizeof(int), cudaMemcpyDeviceToHost, h->st));
+        EU_CUDA(h, cudaMemcpyAsync(nown.data(), d_nown.p, nown.size()*sizeof(int), cudaMemcpyDeviceToHost, h->st));
+        EU_CUDA(h, cudaStreamSynchronize(h->st));
+        std::vector<int> base(size_t(h->n_slices) + 1), fbase(size_t(h->n_slices));
+        long long rec_total = 0, f_total = 0;
+        for (int s = 0; s < h->n_slices; ++s) {
+            base[size_t(s)] = int(rec_total);
+            fbase[size_t(s)] = int(f_total);
+            rec_total += (long long)width[size_t(s)]*EU_SLICE;
+            f_total += nown[size_t(s)];
+            if (rec_total > INT_MAX) return fail(h, EU_ERR_UNSUPPORTED, "too many half-face records for one GPU (32-bit)");
+        }
+        base[size_t(h->n_slices)] = int(rec_total);
+        h->F = f_total;
+        if ((rc = upload_vec(h, h->d_slice_base, base))) return rc;
+        if ((rc = upload_vec(h, d_fid_base, fbase))) return rc;
+        EU_CUDA(h, h->d_rec.alloc(size_t(rec_total)));
+        eu_launch_assign_fid(g, h->d_owner_hf.p, d_fid_base.p, h->d_fid_of_hf.p, h->st);
+        eu_launch_build_records(g, h->d_owner_hf.p, h->d_fid_of_hf.p, h->d_slice_base.p, h->d_rec.p, h->st);
+        const size_t F = size_t(std::max<long long>(h->F, 1));
+        EU_CUDA(h, h->d_q.alloc(F));
+        EU_CUDA(h, h->d_G.alloc(F));
+        EU_CUDA(h, h->d_T.alloc(F));
+        EU_CUDA(h, h->d_nn.alloc(F));
+        EU_CUDA(h, h->d_pcscale.alloc(n));
+        EU_CUDA(h, h->d_rock8.alloc(n));
+        eu_launch_pcscale(g, h->tab, h->d_pcscale.p, h->d_rock8.p, h->st);
+        EU_CUDA(h, cudaStreamSynchronize(h->st));
+    }
+    // state
+    for (int k = 0; k < 2; ++k) {
+        EU_CUDA(h, h->d_S[k].alloc(n));
+        EU_CUDA(h, h->d_pc[k].alloc(n));
+        EU_CUDA(h, cudaMemsetAsync(h->d_S[k].p, 0, n*sizeof(double), h->st));
+        EU_CUDA(h, cudaMemsetAsync(h->d_pc[k].p, 0, n*sizeof(double), h->st));
+    }
+    EU_CUDA(h, h->d_S_init.alloc(n));
+    EU_CUDA(h, h->d_hf_flux.alloc(H));
+    EU_CUDA(h, h->d_residual.alloc(n));
+    EU_CUDA(h, h->d_block_min.alloc(size_t(eu_cfl_blocks(h->n_local))));
+    EU_CUDA(h, h->d_fail_key.alloc(1));
+    EU_CUDA(h, cudaStreamSynchronize(h->st));
+    EU_CUDA(h, cudaGetLastError());
+    h->grid_open = false;
+    h->grid_ready = true;
+    h->cur = 0;
+    return EU_OK;
+}
+
+int eu_local_cells(eu_handle h) { return h ? h->n_local : 0; }
+long long eu_local_halffaces(eu_handle h) { return h ? h->H : 0; }
+
+int eu_upload_saturation(eu_handle h, const double* saturation)
+{
+    if (!h || !saturation) return EU_ERR_ARG;
+    if (!h->grid_ready) return fail(h, EU_ERR_ARG, "grid not ready");
+    EU_CUDA(h, cudaSetDevice(h->cfg.device));
+    EU_CUDA(h, cudaMemcpyAsync(h->d_S[h->cur].p, saturation, size_t(h->n_local)*sizeof(double), cudaMemcpyHostToDevice, h->st));
+    EU_CUDA(h, cudaStreamSynchronize(h->st));
+    return EU_OK;
+}
+
+int eu_upload_state(eu_handle h, const double* saturation, const double* hf_flux)
+{
+    if (!h || !hf_flux) return EU_ERR_ARG;
+    if (!h->grid_ready) return fail(h, EU_ERR_ARG, "grid not ready");
+    EU_CUDA(h, cudaSetDevice(h->cfg.device));
+    EU_CUDA(h, cudaMemcpyAsync(h->d_hf_flux.p, hf_flux, size_t(h->H)*sizeof(double), cudaMemcpyHostToDevice, h->st));
+    if (saturation)
+        EU_CUDA(h, cudaMemcpyAsync(h->d_S[h->cur].p, saturation, size_t(h->n_local)*sizeof(double), cudaMemcpyHostToDevice, h->st));
+    EU_CUDA(h, cudaStreamSynchronize(h->st));
+    h->state_ready = true;
+    return EU_OK;
+}
+
+int eu_download_saturation(eu_handle h, double* saturation)
+{
+    if (!h || !saturation) return EU_ERR_ARG;
+    if (!h->grid_ready) return fail(h, EU_ERR_ARG, "grid not ready");
+    EU_CUDA(h, cudaSetDevice(h->cfg.device));
+    EU_CUDA(h, cudaMemcpyAsync(saturation, h->d_S[h->cur].p, size_t(h->n_local)*sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    EU_CUDA(h, cudaStreamSynchronize(h->st));
+    return EU_OK;
+}
+
+int eu_cfl_times(eu_handle h, const double gravity[3], double out[3])
+{
+    if (!h || !gravity || !out) return EU_ERR_ARG;
+    if (!h->state_ready) return fail(h, EU_ERR_ARG, "no resident state (eu_upload_state)");
+    EU_CUDA(h, cudaSetDevice(h->cfg.device));
+    int zero = 0, launches = 0;
+    int rc = compute_cfl(h, gravity, true, true, true, out, &zero, &launches);
+    if (rc) return rc;
+    if (zero) return fail(h, EU_ERR_CFL_ZERO, "Cfl computation gave dt = 0.0");
+    return EU_OK;
+}
+
+int eu_small_step(eu_handle h, double dt, const double gravity[3], int n_src, const int* src_cell, const double* src_rate,
+                  double* residual_out, int* bad_cell, double* bad_value)
+{
+    if (!h || !gravity) return EU_ERR_ARG;
+    if (!h->state_ready) return fail(h, EU_ERR_ARG, "no resident state (eu_upload_state)");
+    EU_CUDA(h, cudaSetDevice(h->cfg.device));
+    int rc, nls = 0;
+    if ((rc = upload_sources(h, n_src, src_cell, src_rate, &nls))) return rc;
+    int zero = 0, launches = 0;
+    double cfl[3];
+    if ((rc = compute_cfl(h, gravity, false, false, false, cfl, &zero, &launches))) return rc;   // compacts the fluxes
+    if ((rc = ensure_contracted(h, gravity))) return rc;
+    const unsigned long long none = ~0ULL;
+    EU_CUDA(h, cudaMemcpyAsync(h->d_fail_key.p, &none, sizeof(none), cudaMemcpyHostToDevice, h->st));
+    if (h->mode == EU_MODE_FAST && h->par.method_capillary)
+        eu_launch_fast_pc(h->grid(), h->tab, h->fast(), h->d_S[h->cur].p, h->d_pc[h->cur].p, 0, h->n_local, h->st);
+    EuStepArgs a = step_args(h, dt, gravity, nls, 0);
+    a.residual_out = h->d_residual.p;
+    // ghost entries of the new state keep the old values (single substep, no exchange)
+    EU_CUDA(h, cudaMemcpyAsync(h->d_S[h->cur ^ 1].p, h->d_S[h->cur].p, size_t(h->n_local)*sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+    launch_substep(h, a);
+    h->cur ^= 1;
+    unsigned long long key = none;
+    EU_CUDA(h, cudaMemcpyAsync(&key, h->d_fail_key.p, sizeof(key), cudaMemcpyDeviceToHost, h->st));
+    if (residual_out)
+        EU_CUDA(h, cudaMemcpyAsync(residual_out, h->d_residual.p + h->own_lo, size_t(h->own_hi - h->own_lo)*sizeof(double),
+                                   cudaMemcpyDeviceToHost, h->st));
+    EU_CUDA(h, cudaStreamSynchronize(h->st));
+    EU_CUDA(h, cudaGetLastError());
+    if (bad_cell) *bad_cell = -1;
+    if (key != none) {
+        const int lc = int(key & 0xffffffffu);
+        double v = 0.0;
+        EU_CUDA(h, cudaMemcpy(&v, h->d_S[h->cur].p + lc, sizeof(double), cudaMemcpyDeviceToHost));
+        if (bad_cell) *bad_cell = h->local_to_global(lc);
+        if (bad_value) *bad_value = v;
+        return EU_ERR_SAT_RANGE;
+    }
+    return EU_OK;
+}
+
+int eu_transport_solve_resident(eu_handle h, double time, const double gravity[3], int n_src, const int* src_cell,
+                                const double* src_rate, eu_report* rep)
+{
+    if (!h || !gravity || !rep) return EU_ERR_ARG;
+    if (!h->state_ready) return fail(h, EU_ERR_ARG, "no resident state (eu_upload_state)");
+    EU_CUDA(h, cudaSetDevice(h->cfg.device));
+    std::memset(rep, 0, sizeof(*rep));
+    rep->bad_cell = -1;
+    const eu_params& p = h->par;
+    int rc, nls = 0, launches = 0;
+    if ((rc = upload_sources(h, n_src, src_cell, src_rate, &nls))) return rc;
+
+    // ---- computeCflTime (EulerUpstream_impl.hpp:263-331)
+    int zero = 0;
+    double cfl[3];
+    if ((rc = compute_cfl(h, gravity, p.method_viscous && p.use_cfl_viscous, p.method_gravity && p.use_cfl_gravity,
+                          p.method_capillary && p.use_cfl_capillary, cfl, &zero, &launches))) return rc;
+    rep->cfl_dt[0] = cfl[0]; rep->cfl_dt[1] = cfl[1]; rep->cfl_dt[2] = cfl[2];
+    if (zero && p.method_viscous && p.use_cfl_viscous) {
+        rep->status = EU_ERR_CFL_ZERO;
+        rep->kernel_launches = launches;
+        return fail(h, EU_ERR_CFL_ZERO, "Cfl computation gave dt = 0.0");
+    }
+    double cfl_dt = std::min(std::min(cfl[0], cfl[1]), cfl[2]);
+    cfl_dt *= p.courant_number;
+
+    // ---- number of small steps (:163-172)
+    int nsteps;
+    if (cfl_dt > time) {
+        nsteps = p.minimum_small_steps;
+    } else {
+        double steps = std::min<double>(std::ceil(time/cfl_dt), std::numeric_limits<int>::max());
+        nsteps = (steps != steps) ? std::numeric_limits<int>::min() : int(steps);
+        nsteps = std::max(nsteps, p.minimum_small_steps);
+        nsteps = std::min(nsteps, p.maximum_small_steps);
+    }
+    double dt = time/nsteps;
+
+    if ((rc = ensure_contracted(h, gravity))) return rc;
+    const size_t nbytes = size_t(h->n_local)*sizeof(double);
+    EU_CUDA(h, cudaMemcpyAsync(h->d_S_init.p, h->d_S[h->cur].p, nbytes, cudaMemcpyDeviceToDevice, h->st));   // saturation_initial (:181)
+    // ghost entries of the second buffer: single-rank runs have none; multi-rank exchange fills them
+    EU_CUDA(h, cudaMemcpyAsync(h->d_S[h->cur ^ 1].p, h->d_S[h->cur].p, nbytes, cudaMemcpyDeviceToDevice, h->st));
+
+    const unsigned long long none = ~0ULL;
+    int repeats = 0;
+    const int max_repeats = 10;
+    bool finished = false;
+    while (!finished) {
+        ++rep->attempts;
+        EU_CUDA(h, cudaMemcpyAsync(h->d_fail_key.p, &none, sizeof(none), cudaMemcpyHostToDevice, h->st));
+        if (h->mode == EU_MODE_FAST && p.method_capillary) {
+            eu_launch_fast_pc(h->grid(), h->tab, h->fast(), h->d_S[h->cur].p, h->d_pc[h->cur].p, 0, h->n_local, h->st);
+            ++launches;
+        }
+        const int start = h->cur;
+        EU_CUDA(h, cudaEventRecord(h->ev0, h->st));
+        for (int q = 0; q < nsteps; ++q) {
+            EuStepArgs a = step_args(h, dt, gravity, nls, q);
+            launches += launch_substep(h, a);
+            h->cur ^= 1;
+        }
+        EU_CUDA(h, cudaEventRecord(h->ev1, h->st));
+        unsigned long long key = none;
+        EU_CUDA(h, cudaMemcpyAsync(&key, h->d_fail_key.p, sizeof(key), cudaMemcpyDeviceToHost, h->st));
+        EU_CUDA(h, cudaStreamSynchronize(h->st));
+        EU_CUDA(h, cudaGetLastError());
+        rep->substeps_executed += nsteps;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+        rep->device_ms = ms;
+        if (h->cfg.world_size > 1) {
+            double k = key == none ? -1.0 : double(key >> 32);   // first failing substep on any rank
+            // encode as max over (large - substep) so that the earliest failure wins
+            double enc = key == none ? 0.0 : 4294967296.0 - k;
+            h->allreduce(h->allreduce_user, &enc, 1, 1);
+            if (enc != 0.0 && key == none) key = (unsigned long long)(4294967296.0 - enc) << 32 | 0xffffffffu;
+        }
+        if (key == none) {
+            finished = true;
+        } else {
+            // "Saturation out of range in EulerUpstream: Cell <c>   sat <s>" (:344-346)
+            const int lc = int(key & 0xffffffffu);
+            const int fs = int(key >> 32);
+            if (lc != -1 && unsigned(lc) != 0xffffffffu) {
+                // buffer holding the output of substep fs: fs+1 swaps away from the attempt's start buffer
+                const int buf = start ^ ((fs + 1) & 1);
+                double v = 0.0;
+                EU_CUDA(h, cudaMemcpy(&v, h->d_S[buf].p + lc, sizeof(double), cudaMemcpyDeviceToHost));
+                rep->bad_cell = h->local_to_global(lc);
+                rep->bad_value = v;
+            }
+            ++repeats;
+            if (repeats > max_repeats) {
+                rep->status = EU_ERR_SAT_RANGE;
+                break;
+            }
+            nsteps *= 2;                       // :209-211
+            dt = time/nsteps;
+            EU_CUDA(h, cudaMemcpyAsync(h->d_S[h->cur].p, h->d_S_init.p, nbytes, cudaMemcpyDeviceToDevice, h->st));
+            EU_CUDA(h, cudaMemcpyAsync(h->d_S[h->cur ^ 1].p, h->d_S_init.p, nbytes, cudaMemcpyDeviceToDevice, h->st));
+        }
+    }
+    rep->nsteps = nsteps;
+    rep->dt = dt;
+    rep->kernel_launches = launches;
+    if (rep->status == EU_ERR_SAT_RANGE) {
+        char buf[160];
+        std::snprintf(buf, sizeof(buf), "Saturation out of range in EulerUpstream: Cell %d   sat %.17g", rep->bad_cell, rep->bad_value);
+        return fail(h, EU_ERR_SAT_RANGE, buf);
+    }
+    if (finished) { rep->bad_cell = -1; rep->bad_value = 0.0; }
+    return EU_OK;
+}
+
+int eu_transport_solve(eu_handle h, double* saturation, double time, const double gravity[3], const double* hf_flux,
+                       int n_src, const int* src_cell, const double* src_rate, eu_report* report)
+{
+    if (!h || !saturation || !hf_flux || !report) return EU_ERR_ARG;
+    int rc;
+    if ((rc = eu_upload_state(h, saturation, hf_flux))) return rc;
+    rc = eu_transport_solve_resident(h, time, gravity, n_src, src_cell, src_rate, report);
+    if (rc != EU_OK && rc != EU_ERR_SAT_RANGE) return rc;
+    int rc2 = eu_download_saturation(h, saturation);
+    return rc != EU_OK ? rc : rc2;
+}
+
+int eu_comm_blob_size(eu_handle h) { (void)h; return 0; }
+int eu_comm_export(eu_handle h, void* blob) { (void)blob; return fail(h, EU_ERR_UNSUPPORTED, "multi-GPU exchange not built yet"); }
+int eu_comm_connect(eu_handle h, const void* all_blobs) { (void)all_blobs; return fail(h, EU_ERR_UNSUPPORTED, "multi-GPU exchange not built yet"); }
+int eu_comm_set_allreduce(eu_handle h, eu_allreduce_fn fn, void* user)
+{
+    if (!h) return EU_ERR_ARG;
+    h->allreduce = fn;
+    h->allreduce_user = user;
+    return EU_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,150 @@
+// Internal declarations shared by the translation units of libeuler_b200.so.
+//
+//   eu_api.cu     host side of the C ABI (include/euler_b200.h): upload, step-count logic,
+//                 retry loop, reports                      -- EulerUpstream_impl.hpp:95-218
+//   eu_setup.cu   one-time structure building + STRICT arithmetic kernels, compiled with
+//                 -fmad=false (bit-identical to the reference's operation order)
+//   eu_fast.cu    the FAST substep kernel (pre-contracted face scalars, FMA allowed)
+//
+// Data layout in HBM (per rank; "local" = own + ghost cells in ascending global order):
+//   "fat" static arrays, exactly what the host uploaded (kept for re-contraction when gravity
+//   or the method flags change and for STRICT mode):
+//       hf_offset[n+1] | hf_nbr[H] | hf_area[H] | hf_normal[3H] | hf_centroid[3H]
+//       cell_volume[n] | cell_centroid[3n] | poro[n] | perm[9n] | rock[n]
+//       bnd_kind/sat/partner_hf/partner_cell[nb]      (hf_nbr <= -2 encodes -2-bnd_index)
+//   derived, STRICT:  owner_hf[H], strict list (int2 {owner hf, lo cell}) per half-face,
+//                     porevol[n]
+//   derived, FAST:    SELL-32 records int2 {nbr|code, face id} (slot-major inside a slice of
+//                     32 cells: record of (slot j, lane l) at base[s] + 32*j + l),
+//                     unique-face arrays q[F], G[F], T[F] in (slice, slot, lane) order,
+//                     per cell porevol[n], pcscale[n], rock8[n]
+//   state:            S[2][n] ping-pong, pc[2][n], hf_flux[H]
+#ifndef EU_INTERNAL_H
+#define EU_INTERNAL_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/euler_b200.h"
+
+#define EU_MAX_ROCKS 16
+#define EU_SLICE 32
+#define EU_REC_PAD (-1)
+
+// ---- rock tables in device memory ----------------------------------------------------------
+struct EuTablesDev {
+    int kind;                 // EU_MOB_*
+    int n_rocks;
+    int n_nodes_total;
+    int use_j;
+    double sigma_cos_theta;
+    double visc[2];
+    double delta_rho;
+    const int* offset;        // n_rocks+1
+    const double* s;          // nodes
+    const double* cols[7];    // raw columns (STRICT)
+    // FAST (scalar mobility): mobility = kr/visc at the nodes and its slope per interval,
+    // J nodes and slope; bucket index for the interval search.
+    const double* lam[2];     // lam[phase][node]
+    const double* lam_slope[2];
+    const double* J;
+    const double* J_slope;
+    const int* bucket;        // n_rocks * EU_BUCKETS : lowest interval of each bucket
+};
+#define EU_BUCKETS 64
+
+// ---- grid / structure pointers handed to kernels -----------------------------------------
+struct EuGridDev {
+    int n_local;              // own + ghost
+    int own_lo, own_hi;       // local index range of the cells this rank updates
+    int cell_global0;         // global id = local id + cell_global0 only when contiguous (single range)
+    long long H;
+    const int* hf_offset;
+    const int* hf_nbr;        // local neighbour id, or -2-bnd for boundary half-faces
+    const double* hf_area;
+    const double* hf_normal;
+    const double* hf_centroid;
+    const double* cell_volume;
+    const double* cell_centroid;
+    const double* poro;
+    const double* perm;
+    const int* rock;
+    const int* bnd_kind;
+    const double* bnd_sat;
+    const int* bnd_partner_hf;     // local half-face index of the periodic partner
+    const int* bnd_partner_cell;   // local cell of the periodic partner
+    const int* local_to_global;    // n_local
+};
+
+struct EuStrictDev {
+    const int2* list;         // per half-face slot of a cell: {owner hf, lo cell}, strict order
+    const double* porevol;    // volume*poro
+};
+
+struct EuFastDev {
+    int n_slices;             // slices over all local cells
+    const int* slice_base;    // n_slices+1, record offsets
+    const int2* rec;
+    const double* q;          // compacted flux of the current transportSolve
+    const double* G;
+    const double* T;
+    const double* nn;         // n.n per face, or NULL when all normals are unit to 1e-13
+    const double* porevol;
+    const double* pcscale;
+    const unsigned char* rock8;
+    long long F;
+};
+
+struct EuStepArgs {
+    double dt;
+    int method_viscous, method_gravity, method_capillary;
+    int check_sat, clamp_sat;
+    int substep;              // index inside the attempt, for the failure key
+    int n_src;
+    const int* src_cell;      // local cell ids, ascending
+    const double* src_rate;
+    const double* S_in;
+    double* S_out;
+    const double* pc_in;      // FAST: pc(S_in) for all local cells; STRICT: scratch filled by k_strict_pc
+    double* pc_out;
+    double* residual_out;     // optional
+    unsigned long long* fail_key;   // min over failing (substep<<32 | local cell)
+    double gravity[3];
+};
+
+// ---- launchers implemented in eu_setup.cu (all -fmad=false) --------------------------------
+struct EuSetupOut;   // opaque to eu_fast.cu
+void eu_launch_translate_nbr(int* hf_nbr, long long H, const int* range_first, const int* range_count,
+                             const int* range_local, int n_ranges, cudaStream_t st);
+void eu_launch_owner(const EuGridDev& g, int* owner_hf, int* err_flag, cudaStream_t st);
+void eu_launch_strict_list(const EuGridDev& g, const int* owner_hf, int2* list, cudaStream_t st);
+void eu_launch_porevol(const EuGridDev& g, double* porevol, cudaStream_t st);
+void eu_launch_slice_count(const EuGridDev& g, const int* owner_hf, int* slice_width, int* slice_nown, cudaStream_t st);
+void eu_launch_assign_fid(const EuGridDev& g, const int* owner_hf, const int* slice_fid_base, int* fid_of_hf, cudaStream_t st);
+void eu_launch_build_records(const EuGridDev& g, const int* owner_hf, const int* fid_of_hf, const int* slice_base,
+                             int2* rec, cudaStream_t st);
+void eu_launch_contract(const EuGridDev& g, const EuTablesDev& t, const int* owner_hf, const int* fid_of_hf,
+                        const double gravity[3], int method_gravity, double* G, double* T, double* nn,
+                        double* nn_maxdev, cudaStream_t st);
+void eu_launch_pcscale(const EuGridDev& g, const EuTablesDev& t, double* pcscale, unsigned char* rock8, cudaStream_t st);
+// CFL terms (CflCalculator.hpp); results are block minima reduced to out[0]
+void eu_launch_cfl_velocity_compact(const EuGridDev& g, double cfl_factor, const double* hf_flux, const int* fid_of_hf,
+                                    double* q, double* block_min, int* zero_flag, double* out, cudaStream_t st);
+void eu_launch_cfl_gravity(const EuGridDev& g, const EuTablesDev& t, double cfl_factor, const double gravity[3],
+                           double* block_min, double* out, cudaStream_t st);
+void eu_launch_cfl_capillary(const EuGridDev& g, double cfl_factor, double* block_min, double* out, cudaStream_t st);
+int eu_cfl_blocks(int n_cells);
+// STRICT substep
+void eu_launch_strict_pc(const EuGridDev& g, const EuTablesDev& t, const double* S, double* pc, cudaStream_t st);
+void eu_launch_strict_step(const EuGridDev& g, const EuTablesDev& t, const EuStrictDev& s, const double* hf_flux,
+                           const EuStepArgs& a, cudaStream_t st);
+// ---- eu_fast.cu ------------------------------------------------------------------------------
+void eu_launch_fast_pc(const EuGridDev& g, const EuTablesDev& t, const EuFastDev& f, const double* S, double* pc,
+                       int lo, int hi, cudaStream_t st);
+void eu_launch_fast_step(const EuGridDev& g, const EuTablesDev& t, const EuFastDev& f, const EuStepArgs& a,
+                         int slice_lo, int slice_hi, int n_sms, cudaStream_t st);
+size_t eu_fast_smem_bytes(const EuTablesDev& t);
+
+#endif
