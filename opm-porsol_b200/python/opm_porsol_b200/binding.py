@@ -299,6 +299,30 @@ class EulerUpstream:
             self._check(self.L.eu_grid_append(self.h, C.byref(ch)))
         self._check(self.L.eu_grid_end(self.h))
 
+    def initObjChunks(self, fluid_case, n_global, n_local, n_local_hf, chunks, cfl_factors):
+        """Streaming form of initObj for grids too large to hold as one Case: ``chunks`` yields
+        dicts in eu_grid_chunk layout (global cell ids), e.g. synth.c4_slab(...).  ``cfl_factors``
+        must be given (they depend on min-perm / max-poro over the whole grid)."""
+        self.case = fluid_case
+        fluid, keep = make_fluid(fluid_case, cfl_factors)
+        self._fluid_keep = keep
+        self.cfl_factors = np.array(fluid.cfl_factor[:])
+        self._check(self.L.eu_grid_begin(self.h, int(n_global), int(n_local), int(n_local_hf)))
+        self._check(self.L.eu_set_fluid(self.h, C.byref(fluid)))
+        for d in chunks:
+            ch = _Chunk()
+            ch.first_cell, ch.n_cells = int(d["first_cell"]), int(d["n_cells"])
+            ch.hf_count, ch.hf_neighbour = _i(d["hf_count"]), _i(d["hf_neighbour"])
+            ch.hf_area, ch.hf_normal, ch.hf_centroid = _d(d["hf_area"]), _d(d["hf_normal"]), _d(d["hf_centroid"])
+            ch.n_bnd = int(d["bnd_hf"].shape[0])
+            ch.bnd_hf, ch.bnd_kind, ch.bnd_sat = _i(d["bnd_hf"]), _i(d["bnd_kind"]), _d(d["bnd_sat"])
+            ch.bnd_partner_cell, ch.bnd_partner_face = _i(d["bnd_partner_cell"]), _i(d["bnd_partner_face"])
+            ch.cell_volume, ch.cell_centroid = _d(d["cell_volume"]), _d(d["cell_centroid"])
+            ch.porosity, ch.permeability = _d(d["porosity"]), _d(d["permeability"])
+            ch.rock_id = _i(d["rock_id"]) if d.get("rock_id") is not None else None
+            self._check(self.L.eu_grid_append(self.h, C.byref(ch)))
+        self._check(self.L.eu_grid_end(self.h))
+
     # -- EulerUpstream::transportSolve (:151-218); host buffers in, host buffers out
     def transportSolve(self, saturation, time, gravity, hf_flux, injection_rates=None, raise_on_error=True):
         sc, sr = self._sources(injection_rates)

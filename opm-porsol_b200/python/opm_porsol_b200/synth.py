@@ -106,32 +106,25 @@ def _i32(a):
 # ----------------------------------------------------------------------------------
 # Cartesian grids
 # ----------------------------------------------------------------------------------
-def cartesian_grid(nx, ny, nz, dx=1.0, dy=1.0, dz=1.0, unique_bids=True, periodic=(False, False, False),
-                   k0=0, k1=None, nz_total=None):
-    """Flat arrays of an nx*ny*nz Cartesian grid, cell index c = i + nx*(j + ny*k).
-
-    Boundary ids follow CpGrid: 1..6 for the sides when not unique, else 1..#boundary faces in
-    half-face order (setupBoundaryConditions.hpp:48-49).  ``periodic`` marks side pairs whose
-    boundary ids are periodic partners (only with unique ids, EulerUpstreamResidual.hpp:110-112).
-    Returns a dict of arrays plus the bid tables.
-    """
-    N = nx*ny*nz
-    c = np.arange(N, dtype=np.int64)
+def _cartesian_slab_arrays(nx, ny, nz, dx, dy, dz, k0, k1):
+    """Half-face arrays of the cells with k in [k0, k1) of an nx*ny*nz Cartesian grid."""
+    n = nx*ny*(k1 - k0)
+    c = np.arange(nx*ny*k0, nx*ny*k1, dtype=np.int64)
     i = c % nx
     j = (c // nx) % ny
     k = c // (nx*ny)
-    nbr = np.empty((N, 6), dtype=np.int64)
+    nbr = np.empty((n, 6), dtype=np.int64)
     nbr[:, 0] = np.where(i > 0, c - 1, -1)
     nbr[:, 1] = np.where(i < nx - 1, c + 1, -1)
     nbr[:, 2] = np.where(j > 0, c - nx, -1)
     nbr[:, 3] = np.where(j < ny - 1, c + nx, -1)
     nbr[:, 4] = np.where(k > 0, c - nx*ny, -1)
     nbr[:, 5] = np.where(k < nz - 1, c + nx*ny, -1)
-    area = np.empty((N, 6))
+    area = np.empty((n, 6))
     area[:, 0:2] = dy*dz
     area[:, 2:4] = dx*dz
     area[:, 4:6] = dx*dy
-    normal = np.zeros((N, 6, 3))
+    normal = np.zeros((n, 6, 3))
     normal[:, 0, 0] = -1.0
     normal[:, 1, 0] = 1.0
     normal[:, 2, 1] = -1.0
@@ -146,6 +139,19 @@ def cartesian_grid(nx, ny, nz, dx=1.0, dy=1.0, dz=1.0, unique_bids=True, periodi
     fc[:, 3, 1] = (j + 1)*dy
     fc[:, 4, 2] = k*dz
     fc[:, 5, 2] = (k + 1)*dz
+    return c, nbr, area, normal, fc, cc
+
+
+def cartesian_grid(nx, ny, nz, dx=1.0, dy=1.0, dz=1.0, unique_bids=True, periodic=(False, False, False)):
+    """Flat arrays of an nx*ny*nz Cartesian grid, cell index c = i + nx*(j + ny*k).
+
+    Boundary ids follow CpGrid: 1..6 for the sides when not unique, else 1..#boundary faces in
+    half-face order (setupBoundaryConditions.hpp:48-49).  ``periodic`` marks side pairs whose
+    boundary ids are periodic partners (only with unique ids, EulerUpstreamResidual.hpp:110-112).
+    Returns a dict of arrays plus the bid tables.
+    """
+    N = nx*ny*nz
+    c, nbr, area, normal, fc, cc = _cartesian_slab_arrays(nx, ny, nz, dx, dy, dz, 0, nz)
     bnd = nbr < 0
     bid = np.zeros((N, 6), dtype=np.int64)
     if unique_bids:
@@ -509,3 +515,62 @@ def random_geometry_case(nx, ny, nz, seed=1, periodic=(False, False, False), n_r
                      mobility_kind=mobility_kind,
                      sat0=0.05 + 0.9*rs.random(N), gravity=[0.3, -0.2, -9.80665],
                      hf_flux=constant_velocity_flux(g, v), src_cell=src_cell, src_rate=src_rate, time=3600.0)
+
+
+# ----------------------------------------------------------------------------------
+# Streaming generation of the big Cartesian configuration (C4) in z-slabs, so that neither
+# the host nor the upload ever holds the full 27 GB "fat" grid description at once.
+# ----------------------------------------------------------------------------------
+def plane_uniform(seed, k, n):
+    """Uniforms of plane k of a field: independent of how the grid is chunked or partitioned."""
+    return mt_uniform(seed*1000003 + k, n)
+
+
+def c4_slab(nx, ny, nz, k0, k1, seed=44, velocity=(1e-6, 5e-7, 2.5e-7), dirichlet_sat=1.0):
+    """Cells with k in [k0, k1) of the C4 configuration (512x512x256 Cartesian, dx = 1 m,
+    lognormal K with kz = 0.1 kx, phi in [0.05, 0.30], default Dirichlet S = 1 boundaries,
+    constant-velocity flux, S0 = 0.3 +- 0.1).  Returns a dict in eu_grid_chunk form (global ids)
+    plus ``sat0`` and ``hf_flux`` for these cells."""
+    npl = nx*ny
+    c, nbr, area, normal, fc, cc = _cartesian_slab_arrays(nx, ny, nz, 1.0, 1.0, 1.0, k0, k1)
+    n = c.shape[0]
+    kx = np.empty(n)
+    poro = np.empty(n)
+    sat0 = np.empty(n)
+    for k in range(k0, k1):
+        sl = slice((k - k0)*npl, (k - k0 + 1)*npl)
+        u1 = plane_uniform(seed, k, npl)
+        u2 = plane_uniform(seed + 7, k, npl)
+        z = np.sqrt(-2.0*np.log(1.0 - u1))*np.cos(2.0*np.pi*u2)
+        kx[sl] = np.exp(np.log(100.0*MILLIDARCY) + z)
+        poro[sl] = 0.05 + 0.25*plane_uniform(seed + 1, k, npl)
+        sat0[sl] = 0.3 + 0.2*(plane_uniform(seed + 2, k, npl) - 0.5)
+    perm = np.zeros((n, 9))
+    perm[:, 0] = kx
+    perm[:, 4] = kx
+    perm[:, 8] = 0.1*kx
+    nbr_flat = nbr.reshape(-1)
+    bnd_hf = np.nonzero(nbr_flat < 0)[0]
+    nrm = normal.reshape(-1, 3)
+    a = area.reshape(-1)
+    flux = ((velocity[0]*nrm[:, 0] + velocity[1]*nrm[:, 1]) + velocity[2]*nrm[:, 2])*a
+    return dict(
+        first_cell=int(c[0]), n_cells=n,
+        hf_count=_i32(np.full(n, 6)), hf_neighbour=_i32(nbr_flat),
+        hf_area=_f64(a), hf_normal=_f64(nrm), hf_centroid=_f64(fc.reshape(-1, 3)),
+        bnd_hf=_i32(bnd_hf), bnd_kind=_i32(np.full(bnd_hf.shape[0], 1)),
+        bnd_sat=_f64(np.full(bnd_hf.shape[0], dirichlet_sat)),
+        bnd_partner_cell=_i32(np.full(bnd_hf.shape[0], -1)), bnd_partner_face=_i32(np.full(bnd_hf.shape[0], -1)),
+        cell_volume=_f64(np.ones(n)), cell_centroid=_f64(cc), porosity=_f64(poro), permeability=_f64(perm),
+        rock_id=_i32(np.zeros(n)), sat0=_f64(sat0), hf_flux=_f64(flux),
+    )
+
+
+def c4_fluid_case(capillary=False):
+    """The fluid/rock/solver-parameter part of C4 as a tiny Case (no grid arrays)."""
+    g = cartesian_grid(1, 1, 1, unique_bids=False)
+    perm = np.zeros((1, 9))
+    perm[0, [0, 4, 8]] = 100.0*MILLIDARCY
+    return make_case("C4-fluid", g, poro=np.full(1, 0.2), perm=perm, rock_id=np.zeros(1, dtype=np.int32),
+                     rocks=[corey_table()], sat0=np.zeros(1), gravity=[0.0, 0.0, -9.80665],
+                     hf_flux=np.zeros(6), method_capillary=capillary)
