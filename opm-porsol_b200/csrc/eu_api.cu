@@ -76,13 +76,16 @@ struct eu_solver {
     eu_fluid fluid;
     std::vector<int> h_tab_offset;
     std::vector<double> h_tab_s, h_tab_cols[7];
-    DevBuf<int> d_tab_offset, d_bucket;
-    DevBuf<double> d_tab_s, d_tab_cols[7], d_lam[2], d_lam_slope[2], d_J, d_J_slope;
+    DevBuf<int> d_tab_offset;
+    DevBuf<unsigned char> d_fbucket;
+    DevBuf<double> d_tab_s, d_tab_cols[7], d_fcoef, d_fjcoef, d_fxb;
+    int n_buckets = 0;
+    bool fast_tables_ok = true;
     EuTablesDev tab;
     // ---- derived
     DevBuf<int> d_owner_hf, d_fid_of_hf, d_slice_base, d_flags;
     DevBuf<int2> d_strict_list, d_rec;
-    DevBuf<double> d_porevol, d_pcscale, d_q, d_G, d_T, d_nn;
+    DevBuf<double> d_porevol, d_inv_porevol, d_pcscale, d_q, d_G, d_T, d_nn;
     DevBuf<unsigned char> d_rock8;
     long long F = 0;
     int n_slices = 0;
@@ -124,7 +127,7 @@ struct eu_solver {
         EuFastDev f;
         f.n_slices = n_slices; f.slice_base = d_slice_base.p; f.rec = d_rec.p;
         f.q = d_q.p; f.G = d_G.p; f.T = d_T.p; f.nn = use_nn ? d_nn.p : nullptr;
-        f.porevol = d_porevol.p; f.pcscale = d_pcscale.p; f.rock8 = d_rock8.p; f.F = F;
+        f.inv_porevol = d_inv_porevol.p; f.pcscale = d_pcscale.p; f.rock8 = d_rock8.p; f.F = F;
         return f;
     }
     int global_to_local(int gcell) const
@@ -204,9 +207,9 @@ void set_tables_struct(eu_handle h)
     t.delta_rho = h->fluid.density[0] - h->fluid.density[1];       // densityDifference()
     t.offset = h->d_tab_offset.p; t.s = h->d_tab_s.p;
     for (int k = 0; k < 7; ++k) t.cols[k] = h->d_tab_cols[k].p;
-    t.lam[0] = h->d_lam[0].p; t.lam[1] = h->d_lam[1].p;
-    t.lam_slope[0] = h->d_lam_slope[0].p; t.lam_slope[1] = h->d_lam_slope[1].p;
-    t.J = h->d_J.p; t.J_slope = h->d_J_slope.p; t.bucket = h->d_bucket.p;
+    t.inv_visc[0] = 1.0/h->fluid.viscosity[0]; t.inv_visc[1] = 1.0/h->fluid.viscosity[1];
+    t.n_buckets = h->n_buckets;
+    t.fcoef = h->d_fcoef.p; t.fjcoef = h->d_fjcoef.p; t.fxb = h->d_fxb.p; t.fbucket = h->d_fbucket.p;
 }
 
 int ensure_contracted(eu_handle h, const double gravity[3])
@@ -529,43 +532,70 @@ int eu_set_fluid(eu_handle h, const eu_fluid* f)
     if ((rc = upload_vec(h, h->d_tab_offset, h->h_tab_offset))) return rc;
     if ((rc = upload_vec(h, h->d_tab_s, h->h_tab_s))) return rc;
     for (int k = 0; k < 7; ++k) if ((rc = upload_vec(h, h->d_tab_cols[k], h->h_tab_cols[k]))) return rc;
-    // FAST tables (scalar mobility): mobility = kr/viscosity at the nodes, slope per interval
+    // FAST tables (scalar mobility): mobility = kr/viscosity and J per interval in intercept/slope form
+    h->fast_tables_ok = true;
+    h->n_buckets = 0;
     if (f->mobility_kind == EU_MOB_SCALAR && f->n_rocks > 0) {
         const int nn = int(h->h_tab_s.size());
-        std::vector<double> lam[2], sl[2], J(nn), Js(nn, 0.0);
-        std::vector<int> bucket(size_t(f->n_rocks)*EU_BUCKETS, 0);
-        for (int p = 0; p < 2; ++p) { lam[p].resize(nn); sl[p].assign(nn, 0.0); }
-        for (int i = 0; i < nn; ++i) {
-            lam[0][i] = h->h_tab_cols[0][i]/f->viscosity[0];
-            lam[1][i] = h->h_tab_cols[1][i]/f->viscosity[1];
-            J[i] = h->h_tab_cols[2][i];
-        }
+        const double inf = std::numeric_limits<double>::infinity();
+        std::vector<double> coef(size_t(4)*nn, 0.0), jcoef(size_t(2)*nn, 0.0), xb(h->h_tab_s);
         for (int r = 0; r < f->n_rocks; ++r) {
             const int b = h->h_tab_offset[r], e = h->h_tab_offset[r + 1];
             for (int i = b; i + 1 < e; ++i) {
-                const double dx = h->h_tab_s[i + 1] - h->h_tab_s[i];
-                sl[0][i] = (lam[0][i + 1] - lam[0][i])/dx;
-                sl[1][i] = (lam[1][i + 1] - lam[1][i])/dx;
-                Js[i] = (J[i + 1] - J[i])/dx;
+                const double x0 = h->h_tab_s[i], dx = h->h_tab_s[i + 1] - x0;
+                if (!(dx > 0.0)) return fail(h, EU_ERR_ARG, "rock table saturations must be strictly increasing");
+                for (int p = 0; p < 2; ++p) {
+                    const double y0 = h->h_tab_cols[p][i]/f->viscosity[p], y1 = h->h_tab_cols[p][i + 1]/f->viscosity[p];
+                    const double slope = (y1 - y0)/dx;
+                    coef[size_t(4)*i + 2*p] = y0 - slope*x0;
+                    coef[size_t(4)*i + 2*p + 1] = slope;
+                }
+                const double j0 = h->h_tab_cols[2][i], slope = (h->h_tab_cols[2][i + 1] - j0)/dx;
+                jcoef[size_t(2)*i] = j0 - slope*x0;
+                jcoef[size_t(2)*i + 1] = slope;
             }
-            for (int k = 1; k < EU_BUCKETS; ++k) {
-                bucket[size_t(r)*EU_BUCKETS + k] = table_index_host(&h->h_tab_s[b], e - b, double(k)/EU_BUCKETS);
+            xb[size_t(e) - 1] = inf;
+        }
+        // buckets over [0,1): smallest power of two such that no bucket holds two interior nodes
+        int nb = 64;
+        for (; nb <= 4096; nb *= 2) {
+            bool ok = true;
+            for (int r = 0; r < f->n_rocks && ok; ++r) {
+                const int b = h->h_tab_offset[r], e = h->h_tab_offset[r + 1];
+                int prev_bucket = -1;
+                for (int i = b + 1; i + 1 < e; ++i) {                   // interior nodes
+                    int k = int(std::floor(h->h_tab_s[i]*nb));
+                    k = std::min(std::max(k, 0), nb - 1);
+                    if (k == prev_bucket) { ok = false; break; }
+                    prev_bucket = k;
+                }
             }
+            if (ok) break;
         }
-        for (int p = 0; p < 2; ++p) {
-            if ((rc = upload_vec(h, h->d_lam[p], lam[p]))) return rc;
-            if ((rc = upload_vec(h, h->d_lam_slope[p], sl[p]))) return rc;
+        if (nb > 4096) {
+            h->fast_tables_ok = false;          // nodes closer than 1/4096: FAST search not applicable
+        } else {
+            h->n_buckets = nb;
+            std::vector<unsigned char> bucket(size_t(f->n_rocks)*nb, 0);
+            for (int r = 0; r < f->n_rocks; ++r) {
+                const int b = h->h_tab_offset[r], e = h->h_tab_offset[r + 1];
+                for (int k = 1; k < nb; ++k)
+                    bucket[size_t(r)*nb + k] = (unsigned char)table_index_host(&h->h_tab_s[b], e - b, double(k)/nb);
+            }
+            if ((rc = upload_vec(h, h->d_fbucket, bucket))) return rc;
+            if ((rc = upload_vec(h, h->d_fcoef, coef))) return rc;
+            if ((rc = upload_vec(h, h->d_fjcoef, jcoef))) return rc;
+            if ((rc = upload_vec(h, h->d_fxb, xb))) return rc;
         }
-        if ((rc = upload_vec(h, h->d_J, J))) return rc;
-        if ((rc = upload_vec(h, h->d_J_slope, Js))) return rc;
-        if ((rc = upload_vec(h, h->d_bucket, bucket))) return rc;
     }
     set_tables_struct(h);
     h->fluid_set = true;
     h->contracted = false;
     h->cfl_cap_valid = h->cfl_grav_valid = false;
     if (h->cfg.mode == EU_MODE_STRICT) h->mode = EU_MODE_STRICT;
-    else if (f->mobility_kind == EU_MOB_SCALAR) h->mode = EU_MODE_FAST;
+    else if (f->mobility_kind == EU_MOB_SCALAR && h->fast_tables_ok) h->mode = EU_MODE_FAST;
+    else if (f->mobility_kind == EU_MOB_SCALAR && h->cfg.mode == EU_MODE_FAST)
+        return fail(h, EU_ERR_UNSUPPORTED, "FAST mode needs rock-table nodes at least 1/4096 apart");
     else if (h->cfg.mode == EU_MODE_FAST) return fail(h, EU_ERR_UNSUPPORTED, "FAST mode implements scalar mobility only");
     else h->mode = EU_MODE_STRICT;
     return EU_OK;
@@ -680,7 +710,8 @@ int eu_grid_end(eu_handle h)
         EU_CUDA(h, h->d_nn.alloc(F));
         EU_CUDA(h, h->d_pcscale.alloc(n));
         EU_CUDA(h, h->d_rock8.alloc(n));
-        eu_launch_pcscale(g, h->tab, h->d_pcscale.p, h->d_rock8.p, h->st);
+        EU_CUDA(h, h->d_inv_porevol.alloc(n));
+        eu_launch_pcscale(g, h->tab, h->d_pcscale.p, h->d_rock8.p, h->d_inv_porevol.p, h->st);
         EU_CUDA(h, cudaStreamSynchronize(h->st));
     }
     // state

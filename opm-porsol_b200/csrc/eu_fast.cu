@@ -11,6 +11,8 @@
 //   gravity (not on Dirichlet faces) lambda_w lambda_o/(lambda_t) G; capillary with mobilities
 //   at the average saturation (averaged over the two rocks) times T (pc_hi - pc_lo);
 //   residual[lo] -= dS, residual[hi] += dS; source; S += dt*residual/porevol; check/clamp.
+// Per cell the kernel first loads all its records, then issues every gather (neighbour S, pc, face q/G/T)
+// before any arithmetic, so a warp has 6-8 independent loads per lane in flight instead of a chain.
 #include "eu_internal.h"
 
 namespace {
@@ -18,102 +20,222 @@ namespace {
 constexpr int kWarpsPerBlock = 8;
 constexpr int kBlock = kWarpsPerBlock*32;
 
-struct SmemTables {
-    const int* offset;        // n_rocks+1
-    const double* x;          // nodes
-    const double* lam[2];
-    const double* lams[2];
-    const double* J;
-    const double* Js;
-    const unsigned char* bucket;
+// Rock curves in shared memory (FAST mode).  For every rock and table interval j the mobilities and
+// J are kept in intercept/slope form  y(s) = a_j + b_j s  (a_j = y_j - b_j x_j):
+//   coef[j]  = { a_w, b_w, a_o, b_o }   one 32-byte row, two LDS.128
+//   jcoef[j] = { a_J, b_J }
+//   xb[j]    = x_j, with the last node of each rock replaced by +inf (upper bound of the last interval)
+//   bucket[rock*NB + k] = interval containing k/NB (NB chosen on the host so that a bucket holds at most
+//                         one interior node: the interval is bucket or bucket+1)
+// The interval found is exactly the one the reference's binary search returns (first/last interval
+// outside the table).
+extern __shared__ __align__(16) unsigned char eu_smem[];
+
+struct TabLayout {
+    int nn;          // nodes over all rocks
+    int nb;          // buckets per rock
+    int shift;       // unused
+    __device__ __forceinline__ const double4* coef() const { return reinterpret_cast<const double4*>(eu_smem); }
+    __device__ __forceinline__ const double2* jcoef() const { return reinterpret_cast<const double2*>(eu_smem + size_t(32)*nn); }
+    __device__ __forceinline__ const double* xb() const { return reinterpret_cast<const double*>(eu_smem + size_t(48)*nn); }
+    __device__ __forceinline__ const int* offset() const { return reinterpret_cast<const int*>(eu_smem + size_t(56)*nn); }
+    __device__ __forceinline__ const unsigned char* bucket() const { return eu_smem + size_t(56)*nn + 4*(EU_MAX_ROCKS + 2); }
 };
 
-__device__ __forceinline__ size_t align8(size_t v) { return (v + 7) & ~size_t(7); }
-
-__device__ __forceinline__ SmemTables smem_tables_load(const EuTablesDev& t, unsigned char* smem)
+__device__ __forceinline__ void tables_to_smem(const EuTablesDev& t)
 {
-    SmemTables s;
     const int nn = t.n_nodes_total;
-    double* d = reinterpret_cast<double*>(smem);
-    double* x = d;           d += nn;
-    double* l0 = d;          d += nn;
-    double* l1 = d;          d += nn;
-    double* s0 = d;          d += nn;
-    double* s1 = d;          d += nn;
-    double* J = d;           d += nn;
-    double* Js = d;          d += nn;
-    int* off = reinterpret_cast<int*>(d);
-    unsigned char* bucket = reinterpret_cast<unsigned char*>(off + (t.n_rocks + 1 + 1)/2*2);
+    double4* coef = reinterpret_cast<double4*>(eu_smem);
+    double2* jc = reinterpret_cast<double2*>(eu_smem + size_t(32)*nn);
+    double* xb = reinterpret_cast<double*>(eu_smem + size_t(48)*nn);
+    int* off = reinterpret_cast<int*>(eu_smem + size_t(56)*nn);
+    unsigned char* bucket = eu_smem + size_t(56)*nn + 4*(EU_MAX_ROCKS + 2);
     for (int i = threadIdx.x; i < nn; i += blockDim.x) {
-        x[i] = t.s[i];
-        l0[i] = t.lam[0][i];  l1[i] = t.lam[1][i];
-        s0[i] = t.lam_slope[0][i];  s1[i] = t.lam_slope[1][i];
-        J[i] = t.J[i];  Js[i] = t.J_slope[i];
+        coef[i] = make_double4(t.fcoef[4*i], t.fcoef[4*i + 1], t.fcoef[4*i + 2], t.fcoef[4*i + 3]);
+        jc[i] = make_double2(t.fjcoef[2*i], t.fjcoef[2*i + 1]);
+        xb[i] = t.fxb[i];
     }
     for (int i = threadIdx.x; i <= t.n_rocks; i += blockDim.x) off[i] = t.offset[i];
-    for (int i = threadIdx.x; i < t.n_rocks*EU_BUCKETS; i += blockDim.x) bucket[i] = (unsigned char)t.bucket[i];
-    s.offset = off; s.x = x; s.lam[0] = l0; s.lam[1] = l1; s.lams[0] = s0; s.lams[1] = s1; s.J = J; s.Js = Js;
-    s.bucket = bucket;
-    return s;
+    for (int i = threadIdx.x; i < t.n_rocks*t.n_buckets; i += blockDim.x) bucket[i] = t.fbucket[i];
 }
 
-// interval of the rock table containing sat: same answer as the reference's binary search
-// (first/last interval outside the table), found from a 64-bucket index plus a short scan.
-__device__ __forceinline__ int interval(const SmemTables& tb, int rock, double sat)
+template <bool MULTIROCK>
+__device__ __forceinline__ int interval(const TabLayout& L, int rock, double sat)
 {
-    const int b = tb.offset[rock];
-    const int last = tb.offset[rock + 1] - b - 2;        // index of the last interval
-    int k = __double2int_rd(sat*EU_BUCKETS);
-    k = min(max(k, 0), EU_BUCKETS - 1);
-    int j = tb.bucket[rock*EU_BUCKETS + k];
-    while (j < last && sat >= tb.x[b + j + 1]) ++j;
-    return b + j;
+    int k = __double2int_rd(sat*double(L.nb));
+    k = min(max(k, 0), L.nb - 1);
+    const int b = MULTIROCK ? L.offset()[rock] : 0;
+    int j = b + L.bucket()[(MULTIROCK ? rock*L.nb : 0) + k];
+    j += (sat >= L.xb()[j + 1]) ? 1 : 0;
+    return j;
 }
 
-template <bool ROCKS>
+template <bool ROCKS, bool MULTIROCK>
 struct Mob {
     // mobilities of both phases at (rock, sat)
-    static __device__ __forceinline__ void both(const SmemTables& tb, const EuTablesDev& t, int rock, double sat,
+    static __device__ __forceinline__ void both(const TabLayout& L, const EuTablesDev& t, int rock, double sat,
                                                 double& lw, double& lo)
     {
         if (ROCKS) {
-            const int j = interval(tb, rock, sat);
-            const double ds = sat - tb.x[j];
-            lw = fma(tb.lams[0][j], ds, tb.lam[0][j]);
-            lo = fma(tb.lams[1][j], ds, tb.lam[1][j]);
+            const double4 c = L.coef()[interval<MULTIROCK>(L, rock, sat)];
+            lw = fma(c.y, sat, c.x);
+            lo = fma(c.w, sat, c.z);
         } else {
-            lw = sat*sat/t.visc[0];
-            lo = (1.0 - sat)*(1.0 - sat)/t.visc[1];
+            lw = sat*sat*t.inv_visc[0];
+            lo = (1.0 - sat)*(1.0 - sat)*t.inv_visc[1];
         }
     }
-    static __device__ __forceinline__ double one(const SmemTables& tb, const EuTablesDev& t, int phase, int rock, double sat)
+    static __device__ __forceinline__ double pc(const TabLayout& L, int rock, double sat, double scale)
     {
         if (ROCKS) {
-            const int j = interval(tb, rock, sat);
-            return fma(tb.lams[phase][j], sat - tb.x[j], tb.lam[phase][j]);
-        } else {
-            return phase == 0 ? sat*sat/t.visc[0] : (1.0 - sat)*(1.0 - sat)/t.visc[1];
-        }
-    }
-    static __device__ __forceinline__ double pc(const SmemTables& tb, int rock, double sat, double scale)
-    {
-        if (ROCKS) {
-            const int j = interval(tb, rock, sat);
-            return fma(tb.Js[j], sat - tb.x[j], tb.J[j])*scale;
+            const double2 c = L.jcoef()[interval<MULTIROCK>(L, rock, sat)];
+            return fma(c.y, sat, c.x)*scale;
         } else {
             return 1e5*(1.0 - sat);
         }
     }
 };
 
-template <bool ROCKS, bool CAP>
-__global__ void __launch_bounds__(kBlock) k_fast_step(EuGridDev g, EuTablesDev t, EuFastDev f, EuStepArgs a,
-                                                      int slice_lo, int slice_hi)
+// One face of the gather, from the point of view of cell "self" (mobilities lw0/lo0) against the cell or
+// boundary value on the other side (lw1/lo1).  own: self is the lower-index ("lo") cell, whose frame q, G
+// and T are expressed in.  Returns the contribution to residual[self].
+template <bool CAP>
+__device__ __forceinline__ double face_contribution(bool own, bool interior, double q, double qq, double G,
+                                                    double lw0, double lo0, double lw1, double lo1,
+                                                    int method_viscous, int method_gravity,
+                                                    double cap_coef /* lam_w lam_o / lam_t at the average saturation */,
+                                                    double Tdpc /* T*(pc_hi - pc_lo) */)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    SmemTables tb = {};
+    const bool triv_w = G >= 0.0;
+    // mobilities of the trivial (t) and the other (n) phase on both sides
+    const double t0 = triv_w ? lw0 : lo0, t1 = triv_w ? lw1 : lo1;
+    const double n0 = triv_w ? lo0 : lw0, n1 = triv_w ? lo1 : lw1;
+    const bool u_self = (q >= 0.0) == own;                 // upstream cell of the trivial phase is self
+    const double lam_t = u_self ? t0 : t1;
+    const double gfn = triv_w ? -(lam_t*G) : lam_t*G;
+    const bool u2_self = ((q + gfn) >= 0.0) == own;
+    const double lam_n = u2_self ? n0 : n1;
+    const double lw = triv_w ? lam_t : lam_n;
+    const double lo = triv_w ? lam_n : lam_t;
+    double num = method_viscous ? qq : 0.0;
+    if (method_gravity && interior) num = fma(lo, G, num);
+    double dS = lw*num/(lam_t + lam_n);
+    if (CAP && interior) dS = fma(cap_coef, Tdpc, dS);
+    return own ? -dS : dS;
+}
+
+template <bool ROCKS, bool MULTIROCK, bool CAP, bool NN, int W>
+__device__ __forceinline__ double gather_cell(const TabLayout& L, const EuGridDev& g, const EuTablesDev& t,
+                                              const EuFastDev& f, const EuStepArgs& a, const int2* __restrict__ recp,
+                                              int width, int c, double S0, int rock0, double pc0)
+{
+    // phase A: all records of the cell
+    int2 r[W];
+#pragma unroll
+    for (int j = 0; j < W; ++j) r[j] = (j < width) ? __ldg(recp + j*EU_SLICE) : make_int2(EU_REC_PAD, -1);
+    // phase B: every gather of the cell in flight at once
+    double S1[W], q[W], G[W], T[CAP ? W : 1], pc1[CAP ? W : 1], nn[NN ? W : 1];
+    int rk[MULTIROCK ? W : 1];
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+        S1[j] = 0.0; q[j] = 0.0; G[j] = 0.0;
+        if (CAP) { T[j] = 0.0; pc1[j] = 0.0; }
+        if (NN) nn[j] = 1.0;
+        if (MULTIROCK) rk[j] = rock0;
+        if (r[j].x != EU_REC_PAD) {
+            q[j] = __ldg(f.q + r[j].y);
+            G[j] = __ldg(f.G + r[j].y);
+            if (NN) nn[j] = __ldg(f.nn + r[j].y);
+            if (r[j].x >= 0) {
+                S1[j] = __ldg(a.S_in + r[j].x);
+                if (MULTIROCK) rk[j] = __ldg(f.rock8 + r[j].x);
+                if (CAP) { T[j] = __ldg(f.T + r[j].y); pc1[j] = __ldg(a.pc_in + r[j].x); }
+            } else {
+                S1[j] = __ldg(g.bnd_sat + (-2 - r[j].x));
+            }
+        }
+    }
+    // phase C: arithmetic
+    double lw0, lo0;
+    Mob<ROCKS, MULTIROCK>::both(L, t, rock0, S0, lw0, lo0);
+    double acc = 0.0;
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+        if (r[j].x == EU_REC_PAD) continue;
+        const bool interior = r[j].x >= 0;
+        const bool own = !interior || c < r[j].x;
+        const int rk1 = MULTIROCK ? rk[j] : 0;
+        double lw1, lo1;
+        Mob<ROCKS, MULTIROCK>::both(L, t, rk1, S1[j], lw1, lo1);
+        double cap_coef = 0.0, Tdpc = 0.0;
+        if (CAP && interior) {
+            const double Sa = 0.5*(S0 + S1[j]);
+            double lwa, loa;
+            Mob<ROCKS, MULTIROCK>::both(L, t, rock0, Sa, lwa, loa);
+            if (MULTIROCK && rk1 != rock0) {
+                double lwb, lob;
+                Mob<ROCKS, MULTIROCK>::both(L, t, rk1, Sa, lwb, lob);
+                lwa = 0.5*(lwa + lwb);
+                loa = 0.5*(loa + lob);
+            }
+            cap_coef = lwa*loa/(lwa + loa);
+            Tdpc = T[j]*(own ? (pc1[j] - pc0) : (pc0 - pc1[j]));
+        }
+        acc += face_contribution<CAP>(own, interior, q[j], NN ? q[j]*nn[j] : q[j], G[j], lw0, lo0, lw1, lo1,
+                                      a.method_viscous, a.method_gravity, cap_coef, Tdpc);
+    }
+    return acc;
+}
+
+// generic width (cells with more than 8 faces): same arithmetic, one face at a time
+template <bool ROCKS, bool MULTIROCK, bool CAP, bool NN>
+__device__ double gather_cell_loop(const TabLayout& L, const EuGridDev& g, const EuTablesDev& t,
+                                   const EuFastDev& f, const EuStepArgs& a, const int2* __restrict__ recp,
+                                   int width, int c, double S0, int rock0, double pc0)
+{
+    double lw0, lo0;
+    Mob<ROCKS, MULTIROCK>::both(L, t, rock0, S0, lw0, lo0);
+    double acc = 0.0;
+    for (int j = 0; j < width; ++j) {
+        const int2 r = recp[j*EU_SLICE];
+        if (r.x == EU_REC_PAD) continue;
+        const bool interior = r.x >= 0;
+        const bool own = !interior || c < r.x;
+        const double q = f.q[r.y], G = f.G[r.y];
+        const double nn = NN ? f.nn[r.y] : 1.0;
+        const double S1 = interior ? a.S_in[r.x] : g.bnd_sat[-2 - r.x];
+        const int rk = (MULTIROCK && interior) ? f.rock8[r.x] : rock0;
+        double lw1, lo1;
+        Mob<ROCKS, MULTIROCK>::both(L, t, rk, S1, lw1, lo1);
+        double cap_coef = 0.0, Tdpc = 0.0;
+        if (CAP && interior) {
+            const double Sa = 0.5*(S0 + S1);
+            double lwa, loa;
+            Mob<ROCKS, MULTIROCK>::both(L, t, rock0, Sa, lwa, loa);
+            if (MULTIROCK && rk != rock0) {
+                double lwb, lob;
+                Mob<ROCKS, MULTIROCK>::both(L, t, rk, Sa, lwb, lob);
+                lwa = 0.5*(lwa + lwb);
+                loa = 0.5*(loa + lob);
+            }
+            cap_coef = lwa*loa/(lwa + loa);
+            const double pc1 = a.pc_in[r.x];
+            Tdpc = f.T[r.y]*(own ? (pc1 - pc0) : (pc0 - pc1));
+        }
+        acc += face_contribution<CAP>(own, interior, q, q*nn, G, lw0, lo0, lw1, lo1, a.method_viscous, a.method_gravity,
+                                      cap_coef, Tdpc);
+    }
+    return acc;
+}
+
+template <bool ROCKS, bool MULTIROCK, bool CAP, bool NN>
+__global__ void __launch_bounds__(kBlock, 2) k_fast_step(EuGridDev g, EuTablesDev t, EuFastDev f, EuStepArgs a,
+                                                         int slice_lo, int slice_hi)
+{
+    TabLayout L;
+    L.nn = t.n_nodes_total; L.nb = t.n_buckets; L.shift = 0;
     if (ROCKS) {
-        tb = smem_tables_load(t, smem_raw);
+        tables_to_smem(t);
         __syncthreads();
     }
     {
@@ -129,108 +251,57 @@ __global__ void __launch_bounds__(kBlock) k_fast_step(EuGridDev g, EuTablesDev t
         const bool active = (c >= g.own_lo) && (c < g.own_hi);
         const int base = f.slice_base[s];
         const int width = (f.slice_base[s + 1] - base) >> 5;
-        double S0 = 0.0, pc0 = 0.0;
-        int rock0 = 0;
-        if (active) {
-            S0 = a.S_in[c];
-            if (ROCKS) rock0 = f.rock8[c];
-            if (CAP) pc0 = a.pc_in[c];
-        }
-        double acc = 0.0;
+        if (!active) continue;
+        const double S0 = a.S_in[c];
+        const int rock0 = MULTIROCK ? f.rock8[c] : 0;
+        const double pc0 = CAP ? a.pc_in[c] : 0.0;
+        const double inv_pv = f.inv_porevol[c];
         const int2* __restrict__ recp = f.rec + base + lane;
-        for (int j = 0; j < width; ++j) {
-            const int2 r = recp[j*EU_SLICE];
-            if (!active || r.x == EU_REC_PAD) continue;
-            const double q = f.q[r.y];
-            const double G = f.G[r.y];
-            double S1, pc1 = 0.0;
-            int rock1 = rock0;
-            bool own = true, interior = true;
-            if (r.x >= 0) {
-                S1 = a.S_in[r.x];
-                if (ROCKS) rock1 = f.rock8[r.x];
-                if (CAP) pc1 = a.pc_in[r.x];
-                own = c < r.x;
-            } else {
-                S1 = g.bnd_sat[-2 - r.x];
-                interior = false;
+        double acc;
+        if (width <= 6)      acc = gather_cell<ROCKS, MULTIROCK, CAP, NN, 6>(L, g, t, f, a, recp, width, c, S0, rock0, pc0);
+        else if (width <= 8) acc = gather_cell<ROCKS, MULTIROCK, CAP, NN, 8>(L, g, t, f, a, recp, width, c, S0, rock0, pc0);
+        else                 acc = gather_cell_loop<ROCKS, MULTIROCK, CAP, NN>(L, g, t, f, a, recp, width, c, S0, rock0, pc0);
+
+        double rate = 0.0;
+        if (a.n_src > 0) {
+            int lo = 0, hi = a.n_src;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (a.src_cell[mid] < c) lo = mid + 1; else hi = mid; }
+            if (lo < a.n_src && a.src_cell[lo] == c) rate = a.src_rate[lo];
+            if (rate < 0.0) {
+                double lw, lo_;
+                Mob<ROCKS, MULTIROCK>::both(L, t, rock0, S0, lw, lo_);
+                rate *= lw/(lw + lo_);
             }
-            // (lo, hi) ordering
-            const double S_lo = own ? S0 : S1, S_hi = own ? S1 : S0;
-            const int r_lo = own ? rock0 : rock1, r_hi = own ? rock1 : rock0;
-            const bool triv_w = G >= 0.0;
-            const bool u_lo = q >= 0.0;
-            const double lam_t = Mob<ROCKS>::one(tb, t, triv_w ? 0 : 1, u_lo ? r_lo : r_hi, u_lo ? S_lo : S_hi);
-            const double gfn = (triv_w ? -1.0 : 1.0)*(lam_t*G);
-            const bool u2_lo = (q + gfn) >= 0.0;
-            const double lam_n = Mob<ROCKS>::one(tb, t, triv_w ? 1 : 0, u2_lo ? r_lo : r_hi, u2_lo ? S_lo : S_hi);
-            const double lw = triv_w ? lam_t : lam_n;
-            const double lo = triv_w ? lam_n : lam_t;
-            const double inv = 1.0/(lw + lo);
-            double dS = 0.0;
-            if (a.method_viscous) {
-                const double qq = f.nn ? q*f.nn[r.y] : q;
-                dS += lw*(inv*qq);
-            }
-            if (a.method_gravity && interior) dS += lw*(inv*(lo*G));
-            if (CAP && interior) {
-                const double Sa = 0.5*(S_lo + S_hi);
-                double lwa, loa;
-                Mob<ROCKS>::both(tb, t, r_lo, Sa, lwa, loa);
-                if (ROCKS && r_hi != r_lo) {
-                    double lwb, lob;
-                    Mob<ROCKS>::both(tb, t, r_hi, Sa, lwb, lob);
-                    lwa = 0.5*(lwa + lwb);
-                    loa = 0.5*(loa + lob);
-                }
-                const double inva = 1.0/(lwa + loa);
-                const double pc_lo = own ? pc0 : pc1, pc_hi = own ? pc1 : pc0;
-                dS += lwa*(inva*(loa*(f.T[r.y]*(pc_hi - pc_lo))));
-            }
-            acc += own ? -dS : dS;
         }
-        if (active) {
-            double rate = 0.0;
-            if (a.n_src > 0) {
-                int lo = 0, hi = a.n_src;
-                while (lo < hi) { const int mid = (lo + hi) >> 1; if (a.src_cell[mid] < c) lo = mid + 1; else hi = mid; }
-                if (lo < a.n_src && a.src_cell[lo] == c) rate = a.src_rate[lo];
-                if (rate < 0.0) {
-                    double lw, lo_;
-                    Mob<ROCKS>::both(tb, t, rock0, S0, lw, lo_);
-                    rate *= lw/(lw + lo_);
+        acc += rate;
+        if (a.residual_out) a.residual_out[c] = acc;
+        double sat = fma(a.dt*acc, inv_pv, S0);
+        if (a.check_sat || a.clamp_sat) {
+            if (sat > 1.0 || sat < 0.0) {
+                if (a.clamp_sat) {
+                    sat = fmax(fmin(sat, 1.0), 0.0);
+                } else if (sat > 1.001 || sat < -0.001) {
+                    atomicMin(a.fail_key, ((unsigned long long)(unsigned)a.substep << 32) | (unsigned)c);
                 }
             }
-            acc += rate;
-            if (a.residual_out) a.residual_out[c] = acc;
-            double sat = S0 + a.dt*acc/f.porevol[c];
-            if (a.check_sat || a.clamp_sat) {
-                if (sat > 1.0 || sat < 0.0) {
-                    if (a.clamp_sat) {
-                        sat = fmax(fmin(sat, 1.0), 0.0);
-                    } else if (sat > 1.001 || sat < -0.001) {
-                        atomicMin(a.fail_key, ((unsigned long long)(unsigned)a.substep << 32) | (unsigned)c);
-                    }
-                }
-            }
-            a.S_out[c] = sat;
-            if (CAP) a.pc_out[c] = Mob<ROCKS>::pc(tb, rock0, sat, ROCKS ? f.pcscale[c] : 1.0);
         }
+        a.S_out[c] = sat;
+        if (CAP) a.pc_out[c] = Mob<ROCKS, MULTIROCK>::pc(L, rock0, sat, ROCKS ? f.pcscale[c] : 1.0);
     }
 }
 
-template <bool ROCKS>
+template <bool ROCKS, bool MULTIROCK>
 __global__ void __launch_bounds__(kBlock) k_fast_pc(EuGridDev g, EuTablesDev t, EuFastDev f,
                                                     const double* __restrict__ S, double* __restrict__ pc, int lo, int hi)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    SmemTables tb = {};
+    TabLayout L;
+    L.nn = t.n_nodes_total; L.nb = t.n_buckets; L.shift = 0;
     if (ROCKS) {
-        tb = smem_tables_load(t, smem_raw);
+        tables_to_smem(t);
         __syncthreads();
     }
     for (int c = lo + blockIdx.x*blockDim.x + threadIdx.x; c < hi; c += gridDim.x*blockDim.x) {
-        pc[c] = Mob<ROCKS>::pc(tb, ROCKS ? f.rock8[c] : 0, S[c], ROCKS ? f.pcscale[c] : 1.0);
+        pc[c] = Mob<ROCKS, MULTIROCK>::pc(L, MULTIROCK ? f.rock8[c] : 0, S[c], ROCKS ? f.pcscale[c] : 1.0);
     }
 }
 
@@ -239,9 +310,7 @@ __global__ void __launch_bounds__(kBlock) k_fast_pc(EuGridDev g, EuTablesDev t, 
 size_t eu_fast_smem_bytes(const EuTablesDev& t)
 {
     if (t.n_rocks == 0) return 0;
-    size_t b = size_t(7)*t.n_nodes_total*sizeof(double);
-    b += size_t((t.n_rocks + 1 + 1)/2*2)*sizeof(int);
-    b += size_t(t.n_rocks)*EU_BUCKETS;
+    size_t b = size_t(56)*t.n_nodes_total + 4*(EU_MAX_ROCKS + 2) + size_t(t.n_rocks)*t.n_buckets;
     return (b + 15) & ~size_t(15);
 }
 
@@ -252,30 +321,48 @@ void eu_launch_fast_pc(const EuGridDev& g, const EuTablesDev& t, const EuFastDev
     const size_t smem = eu_fast_smem_bytes(t);
     int blocks = (hi - lo + kBlock - 1)/kBlock;
     if (blocks > 148*8) blocks = 148*8;
-    if (t.n_rocks > 0) k_fast_pc<true><<<blocks, kBlock, smem, st>>>(g, t, f, S, pc, lo, hi);
-    else               k_fast_pc<false><<<blocks, kBlock, 0, st>>>(g, t, f, S, pc, lo, hi);
+    if (t.n_rocks > 1)       k_fast_pc<true, true><<<blocks, kBlock, smem, st>>>(g, t, f, S, pc, lo, hi);
+    else if (t.n_rocks == 1) k_fast_pc<true, false><<<blocks, kBlock, smem, st>>>(g, t, f, S, pc, lo, hi);
+    else                     k_fast_pc<false, false><<<blocks, kBlock, 0, st>>>(g, t, f, S, pc, lo, hi);
+}
+
+template <bool ROCKS, bool MULTIROCK, bool CAP, bool NN>
+static void launch_fast(const EuGridDev& g, const EuTablesDev& t, const EuFastDev& f, const EuStepArgs& a,
+                        int slice_lo, int slice_hi, int n_sms, size_t smem, cudaStream_t st)
+{
+    static int blocks_per_sm = 0;
+    if (blocks_per_sm == 0) {
+        if (smem > 48*1024)
+            cudaFuncSetAttribute(k_fast_step<ROCKS, MULTIROCK, CAP, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_fast_step<ROCKS, MULTIROCK, CAP, NN>, kBlock, smem);
+        if (blocks_per_sm < 1) blocks_per_sm = 1;
+    }
+    // persistent grid: every SM full, capped by the work available
+    const int n = slice_hi - slice_lo;
+    int blocks = n_sms*blocks_per_sm;
+    const int need = (n + kWarpsPerBlock - 1)/kWarpsPerBlock;
+    if (blocks > need) blocks = need;
+    k_fast_step<ROCKS, MULTIROCK, CAP, NN><<<blocks, kBlock, smem, st>>>(g, t, f, a, slice_lo, slice_hi);
+}
+
+template <bool ROCKS, bool MULTIROCK>
+static void launch_fast2(const EuGridDev& g, const EuTablesDev& t, const EuFastDev& f, const EuStepArgs& a,
+                         int slice_lo, int slice_hi, int n_sms, size_t smem, cudaStream_t st)
+{
+    const bool cap = a.method_capillary != 0;
+    const bool nn = f.nn != nullptr;
+    if (cap && nn)       launch_fast<ROCKS, MULTIROCK, true, true>(g, t, f, a, slice_lo, slice_hi, n_sms, smem, st);
+    else if (cap)        launch_fast<ROCKS, MULTIROCK, true, false>(g, t, f, a, slice_lo, slice_hi, n_sms, smem, st);
+    else if (nn)         launch_fast<ROCKS, MULTIROCK, false, true>(g, t, f, a, slice_lo, slice_hi, n_sms, smem, st);
+    else                 launch_fast<ROCKS, MULTIROCK, false, false>(g, t, f, a, slice_lo, slice_hi, n_sms, smem, st);
 }
 
 void eu_launch_fast_step(const EuGridDev& g, const EuTablesDev& t, const EuFastDev& f, const EuStepArgs& a,
                          int slice_lo, int slice_hi, int n_sms, cudaStream_t st)
 {
-    const int n = slice_hi - slice_lo;
-    if (n <= 0) return;
+    if (slice_hi <= slice_lo) return;
     const size_t smem = eu_fast_smem_bytes(t);
-    static bool attr_set = false;
-    if (!attr_set && smem > 48*1024) {
-        cudaFuncSetAttribute(k_fast_step<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_fast_step<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
-    }
-    // persistent grid: a multiple of the SM count, capped by the work available
-    int blocks = n_sms*4;
-    const int need = (n + kWarpsPerBlock - 1)/kWarpsPerBlock;
-    if (blocks > need) blocks = need;
-    const bool rocks = t.n_rocks > 0;
-    const bool cap = a.method_capillary != 0;
-    if (rocks && cap)        k_fast_step<true, true><<<blocks, kBlock, smem, st>>>(g, t, f, a, slice_lo, slice_hi);
-    else if (rocks)          k_fast_step<true, false><<<blocks, kBlock, smem, st>>>(g, t, f, a, slice_lo, slice_hi);
-    else if (cap)            k_fast_step<false, true><<<blocks, kBlock, 0, st>>>(g, t, f, a, slice_lo, slice_hi);
-    else                     k_fast_step<false, false><<<blocks, kBlock, 0, st>>>(g, t, f, a, slice_lo, slice_hi);
+    if (t.n_rocks > 1)       launch_fast2<true, true>(g, t, f, a, slice_lo, slice_hi, n_sms, smem, st);
+    else if (t.n_rocks == 1) launch_fast2<true, false>(g, t, f, a, slice_lo, slice_hi, n_sms, smem, st);
+    else                     launch_fast2<false, false>(g, t, f, a, slice_lo, slice_hi, n_sms, smem, st);
 }

@@ -45,15 +45,15 @@ struct EuTablesDev {
     const int* offset;        // n_rocks+1
     const double* s;          // nodes
     const double* cols[7];    // raw columns (STRICT)
-    // FAST (scalar mobility): mobility = kr/visc at the nodes and its slope per interval,
-    // J nodes and slope; bucket index for the interval search.
-    const double* lam[2];     // lam[phase][node]
-    const double* lam_slope[2];
-    const double* J;
-    const double* J_slope;
-    const int* bucket;        // n_rocks * EU_BUCKETS : lowest interval of each bucket
+    // FAST (scalar mobility): per table interval, mobility = kr/visc and J in intercept/slope form
+    // y(s) = a + b s (see eu_fast.cu), the interval bounds and a bucket index for the interval search.
+    double inv_visc[2];
+    int n_buckets;            // per rock; chosen so that a bucket holds at most one interior node
+    const double* fcoef;      // 4 per node: a_w, b_w, a_o, b_o
+    const double* fjcoef;     // 2 per node: a_J, b_J
+    const double* fxb;        // node abscissae, last node of each rock = +inf
+    const unsigned char* fbucket;   // n_rocks * n_buckets
 };
-#define EU_BUCKETS 64
 
 // ---- grid / structure pointers handed to kernels -----------------------------------------
 struct EuGridDev {
@@ -91,7 +91,7 @@ struct EuFastDev {
     const double* G;
     const double* T;
     const double* nn;         // n.n per face, or NULL when all normals are unit to 1e-13
-    const double* porevol;
+    const double* inv_porevol;   // 1/(volume*poro)
     const double* pcscale;
     const unsigned char* rock8;
     long long F;
@@ -128,7 +128,7 @@ void eu_launch_build_records(const EuGridDev& g, const int* owner_hf, const int*
 void eu_launch_contract(const EuGridDev& g, const EuTablesDev& t, const int* owner_hf, const int* fid_of_hf,
                         const double gravity[3], int method_gravity, double* G, double* T, double* nn,
                         double* nn_maxdev, cudaStream_t st);
-void eu_launch_pcscale(const EuGridDev& g, const EuTablesDev& t, double* pcscale, unsigned char* rock8, cudaStream_t st);
+void eu_launch_pcscale(const EuGridDev& g, const EuTablesDev& t, double* pcscale, unsigned char* rock8, double* inv_porevol, cudaStream_t st);
 // CFL terms (CflCalculator.hpp); results are block minima reduced to out[0]
 void eu_launch_cfl_velocity_compact(const EuGridDev& g, double cfl_factor, const double* hf_flux, const int* fid_of_hf,
                                     double* q, double* block_min, int* zero_flag, double* out, cudaStream_t st);

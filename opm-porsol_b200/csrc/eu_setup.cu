@@ -257,7 +257,8 @@ __global__ void k_contract(EuGridDev g, EuTablesDev t, const int* __restrict__ o
     if (maxdev > 0.0) atomicMax(nn_maxdev_bits, (unsigned long long)__double_as_longlong(maxdev));
 }
 
-__global__ void k_pcscale(EuGridDev g, EuTablesDev t, double* __restrict__ pcscale, unsigned char* __restrict__ rock8)
+__global__ void k_pcscale(EuGridDev g, EuTablesDev t, double* __restrict__ pcscale, unsigned char* __restrict__ rock8,
+                          double* __restrict__ inv_porevol)
 {
     int c = blockIdx.x*blockDim.x + threadIdx.x;
     if (c >= g.n_local) return;
@@ -270,6 +271,7 @@ __global__ void k_pcscale(EuGridDev g, EuTablesDev t, double* __restrict__ pcsca
     }
     pcscale[c] = sc;
     rock8[c] = (unsigned char)g.rock[c];
+    inv_porevol[c] = 1.0/(g.cell_volume[c]*g.poro[c]);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -623,9 +625,10 @@ void eu_launch_contract(const EuGridDev& g, const EuTablesDev& t, const int* own
     k_contract<<<div_up(g.n_local, kThreads), kThreads, 0, st>>>(g, t, owner_hf, fid_of_hf, gravity[0], gravity[1], gravity[2],
                                                                  method_gravity, G, T, nn, (unsigned long long*)nn_maxdev);
 }
-void eu_launch_pcscale(const EuGridDev& g, const EuTablesDev& t, double* pcscale, unsigned char* rock8, cudaStream_t st)
+void eu_launch_pcscale(const EuGridDev& g, const EuTablesDev& t, double* pcscale, unsigned char* rock8, double* inv_porevol,
+                       cudaStream_t st)
 {
-    k_pcscale<<<div_up(g.n_local, kThreads), kThreads, 0, st>>>(g, t, pcscale, rock8);
+    k_pcscale<<<div_up(g.n_local, kThreads), kThreads, 0, st>>>(g, t, pcscale, rock8, inv_porevol);
 }
 int eu_cfl_blocks(int n_cells) { return div_up(n_cells > 0 ? n_cells : 1, kThreads); }
 
