@@ -15,6 +15,8 @@
 // before any arithmetic, so a warp has 6-8 independent loads per lane in flight instead of a chain.
 #include "eu_internal.h"
 
+#include <cstdlib>
+
 namespace {
 
 constexpr int kWarpsPerBlock = 8;
@@ -96,6 +98,21 @@ struct Mob {
     }
 };
 
+// x/d for a positive, normal-range denominator (sum of two mobilities): reciprocal seed + two Newton
+// steps + one residual correction; no special-case branch.  Relative error <= 2^-52.
+__device__ __forceinline__ double div_pos(double x, double d)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    double qv = x*r;
+    const double rem = fma(-d, qv, x);
+    return fma(rem, r, qv);
+}
+
 // One face of the gather, from the point of view of cell "self" (mobilities lw0/lo0) against the cell or
 // boundary value on the other side (lw1/lo1).  own: self is the lower-index ("lo") cell, whose frame q, G
 // and T are expressed in.  Returns the contribution to residual[self].
@@ -119,12 +136,12 @@ __device__ __forceinline__ double face_contribution(bool own, bool interior, dou
     const double lo = triv_w ? lam_n : lam_t;
     double num = method_viscous ? qq : 0.0;
     if (method_gravity && interior) num = fma(lo, G, num);
-    double dS = lw*num/(lam_t + lam_n);
+    double dS = div_pos(lw*num, lam_t + lam_n);
     if (CAP && interior) dS = fma(cap_coef, Tdpc, dS);
     return own ? -dS : dS;
 }
 
-template <bool ROCKS, bool MULTIROCK, bool CAP, bool NN, int W>
+template <bool ROCKS, bool MULTIROCK, bool CAP, bool NN, int W, int B>
 __device__ __forceinline__ double gather_cell(const TabLayout& L, const EuGridDev& g, const EuTablesDev& t,
                                               const EuFastDev& f, const EuStepArgs& a, const int2* __restrict__ recp,
                                               int width, int c, double S0, int rock0, double pc0)
@@ -133,56 +150,61 @@ __device__ __forceinline__ double gather_cell(const TabLayout& L, const EuGridDe
     int2 r[W];
 #pragma unroll
     for (int j = 0; j < W; ++j) r[j] = (j < width) ? __ldg(recp + j*EU_SLICE) : make_int2(EU_REC_PAD, -1);
-    // phase B: every gather of the cell in flight at once
-    double S1[W], q[W], G[W], T[CAP ? W : 1], pc1[CAP ? W : 1], nn[NN ? W : 1];
-    int rk[MULTIROCK ? W : 1];
-#pragma unroll
-    for (int j = 0; j < W; ++j) {
-        S1[j] = 0.0; q[j] = 0.0; G[j] = 0.0;
-        if (CAP) { T[j] = 0.0; pc1[j] = 0.0; }
-        if (NN) nn[j] = 1.0;
-        if (MULTIROCK) rk[j] = rock0;
-        if (r[j].x != EU_REC_PAD) {
-            q[j] = __ldg(f.q + r[j].y);
-            G[j] = __ldg(f.G + r[j].y);
-            if (NN) nn[j] = __ldg(f.nn + r[j].y);
-            if (r[j].x >= 0) {
-                S1[j] = __ldg(a.S_in + r[j].x);
-                if (MULTIROCK) rk[j] = __ldg(f.rock8 + r[j].x);
-                if (CAP) { T[j] = __ldg(f.T + r[j].y); pc1[j] = __ldg(a.pc_in + r[j].x); }
-            } else {
-                S1[j] = __ldg(g.bnd_sat + (-2 - r[j].x));
-            }
-        }
-    }
-    // phase C: arithmetic
     double lw0, lo0;
     Mob<ROCKS, MULTIROCK>::both(L, t, rock0, S0, lw0, lo0);
     double acc = 0.0;
 #pragma unroll
-    for (int j = 0; j < W; ++j) {
-        if (r[j].x == EU_REC_PAD) continue;
-        const bool interior = r[j].x >= 0;
-        const bool own = !interior || c < r[j].x;
-        const int rk1 = MULTIROCK ? rk[j] : 0;
-        double lw1, lo1;
-        Mob<ROCKS, MULTIROCK>::both(L, t, rk1, S1[j], lw1, lo1);
-        double cap_coef = 0.0, Tdpc = 0.0;
-        if (CAP && interior) {
-            const double Sa = 0.5*(S0 + S1[j]);
-            double lwa, loa;
-            Mob<ROCKS, MULTIROCK>::both(L, t, rock0, Sa, lwa, loa);
-            if (MULTIROCK && rk1 != rock0) {
-                double lwb, lob;
-                Mob<ROCKS, MULTIROCK>::both(L, t, rk1, Sa, lwb, lob);
-                lwa = 0.5*(lwa + lwb);
-                loa = 0.5*(loa + lob);
+    for (int j0 = 0; j0 < W; j0 += B) {
+        // phase B: every gather of the batch in flight at once
+        double S1[B], q[B], G[B], T[CAP ? B : 1], pc1[CAP ? B : 1], nn[NN ? B : 1];
+        int rk[MULTIROCK ? B : 1];
+#pragma unroll
+        for (int k = 0; k < B; ++k) {
+            const int j = j0 + k;
+            S1[k] = 0.0; q[k] = 0.0; G[k] = 0.0;
+            if (CAP) { T[k] = 0.0; pc1[k] = 0.0; }
+            if (NN) nn[k] = 1.0;
+            if (MULTIROCK) rk[k] = rock0;
+            if (j < W && r[j].x != EU_REC_PAD) {
+                q[k] = __ldg(f.q + r[j].y);
+                G[k] = __ldg(f.G + r[j].y);
+                if (NN) nn[k] = __ldg(f.nn + r[j].y);
+                if (r[j].x >= 0) {
+                    S1[k] = __ldg(a.S_in + r[j].x);
+                    if (MULTIROCK) rk[k] = __ldg(f.rock8 + r[j].x);
+                    if (CAP) { T[k] = __ldg(f.T + r[j].y); pc1[k] = __ldg(a.pc_in + r[j].x); }
+                } else {
+                    S1[k] = __ldg(g.bnd_sat + (-2 - r[j].x));
+                }
             }
-            cap_coef = lwa*loa/(lwa + loa);
-            Tdpc = T[j]*(own ? (pc1[j] - pc0) : (pc0 - pc1[j]));
         }
-        acc += face_contribution<CAP>(own, interior, q[j], NN ? q[j]*nn[j] : q[j], G[j], lw0, lo0, lw1, lo1,
-                                      a.method_viscous, a.method_gravity, cap_coef, Tdpc);
+        // phase C: arithmetic
+#pragma unroll
+        for (int k = 0; k < B; ++k) {
+            const int j = j0 + k;
+            if (j >= W || r[j].x == EU_REC_PAD) continue;
+            const bool interior = r[j].x >= 0;
+            const bool own = !interior || c < r[j].x;
+            const int rk1 = MULTIROCK ? rk[k] : 0;
+            double lw1, lo1;
+            Mob<ROCKS, MULTIROCK>::both(L, t, rk1, S1[k], lw1, lo1);
+            double cap_coef = 0.0, Tdpc = 0.0;
+            if (CAP && interior) {
+                const double Sa = 0.5*(S0 + S1[k]);
+                double lwa, loa;
+                Mob<ROCKS, MULTIROCK>::both(L, t, rock0, Sa, lwa, loa);
+                if (MULTIROCK && rk1 != rock0) {
+                    double lwb, lob;
+                    Mob<ROCKS, MULTIROCK>::both(L, t, rk1, Sa, lwb, lob);
+                    lwa = 0.5*(lwa + lwb);
+                    loa = 0.5*(loa + lob);
+                }
+                cap_coef = div_pos(lwa*loa, lwa + loa);
+                Tdpc = T[k]*(own ? (pc1[k] - pc0) : (pc0 - pc1[k]));
+            }
+            acc += face_contribution<CAP>(own, interior, q[k], NN ? q[k]*nn[k] : q[k], G[k], lw0, lo0, lw1, lo1,
+                                          a.method_viscous, a.method_gravity, cap_coef, Tdpc);
+        }
     }
     return acc;
 }
@@ -218,7 +240,7 @@ __device__ double gather_cell_loop(const TabLayout& L, const EuGridDev& g, const
                 lwa = 0.5*(lwa + lwb);
                 loa = 0.5*(loa + lob);
             }
-            cap_coef = lwa*loa/(lwa + loa);
+            cap_coef = div_pos(lwa*loa, lwa + loa);
             const double pc1 = a.pc_in[r.x];
             Tdpc = f.T[r.y]*(own ? (pc1 - pc0) : (pc0 - pc1));
         }
@@ -228,8 +250,8 @@ __device__ double gather_cell_loop(const TabLayout& L, const EuGridDev& g, const
     return acc;
 }
 
-template <bool ROCKS, bool MULTIROCK, bool CAP, bool NN>
-__global__ void __launch_bounds__(kBlock, 2) k_fast_step(EuGridDev g, EuTablesDev t, EuFastDev f, EuStepArgs a,
+template <bool ROCKS, bool MULTIROCK, bool CAP, bool NN, int B6, int B8, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB) k_fast_step(EuGridDev g, EuTablesDev t, EuFastDev f, EuStepArgs a,
                                                          int slice_lo, int slice_hi)
 {
     TabLayout L;
@@ -258,8 +280,8 @@ __global__ void __launch_bounds__(kBlock, 2) k_fast_step(EuGridDev g, EuTablesDe
         const double inv_pv = f.inv_porevol[c];
         const int2* __restrict__ recp = f.rec + base + lane;
         double acc;
-        if (width <= 6)      acc = gather_cell<ROCKS, MULTIROCK, CAP, NN, 6>(L, g, t, f, a, recp, width, c, S0, rock0, pc0);
-        else if (width <= 8) acc = gather_cell<ROCKS, MULTIROCK, CAP, NN, 8>(L, g, t, f, a, recp, width, c, S0, rock0, pc0);
+        if (width <= 6)      acc = gather_cell<ROCKS, MULTIROCK, CAP, NN, 6, B6>(L, g, t, f, a, recp, width, c, S0, rock0, pc0);
+        else if (width <= 8) acc = gather_cell<ROCKS, MULTIROCK, CAP, NN, 8, B8>(L, g, t, f, a, recp, width, c, S0, rock0, pc0);
         else                 acc = gather_cell_loop<ROCKS, MULTIROCK, CAP, NN>(L, g, t, f, a, recp, width, c, S0, rock0, pc0);
 
         double rate = 0.0;
@@ -326,15 +348,15 @@ void eu_launch_fast_pc(const EuGridDev& g, const EuTablesDev& t, const EuFastDev
     else                     k_fast_pc<false, false><<<blocks, kBlock, 0, st>>>(g, t, f, S, pc, lo, hi);
 }
 
-template <bool ROCKS, bool MULTIROCK, bool CAP, bool NN>
-static void launch_fast(const EuGridDev& g, const EuTablesDev& t, const EuFastDev& f, const EuStepArgs& a,
-                        int slice_lo, int slice_hi, int n_sms, size_t smem, cudaStream_t st)
+template <bool ROCKS, bool MULTIROCK, bool CAP, bool NN, int B6, int B8, int MINB>
+static void launch_variant(const EuGridDev& g, const EuTablesDev& t, const EuFastDev& f, const EuStepArgs& a,
+                           int slice_lo, int slice_hi, int n_sms, size_t smem, cudaStream_t st)
 {
     static int blocks_per_sm = 0;
+    auto kern = k_fast_step<ROCKS, MULTIROCK, CAP, NN, B6, B8, MINB>;
     if (blocks_per_sm == 0) {
-        if (smem > 48*1024)
-            cudaFuncSetAttribute(k_fast_step<ROCKS, MULTIROCK, CAP, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_fast_step<ROCKS, MULTIROCK, CAP, NN>, kBlock, smem);
+        if (smem > 48*1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kBlock, smem);
         if (blocks_per_sm < 1) blocks_per_sm = 1;
     }
     // persistent grid: every SM full, capped by the work available
@@ -342,7 +364,29 @@ static void launch_fast(const EuGridDev& g, const EuTablesDev& t, const EuFastDe
     int blocks = n_sms*blocks_per_sm;
     const int need = (n + kWarpsPerBlock - 1)/kWarpsPerBlock;
     if (blocks > need) blocks = need;
-    k_fast_step<ROCKS, MULTIROCK, CAP, NN><<<blocks, kBlock, smem, st>>>(g, t, f, a, slice_lo, slice_hi);
+    kern<<<blocks, kBlock, smem, st>>>(g, t, f, a, slice_lo, slice_hi);
+}
+
+// EU_FAST_VARIANT (tuning knob, read once): faces per load batch / resident blocks per SM
+static int fast_variant()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("EU_FAST_VARIANT"); v = e ? atoi(e) : 0; }
+    return v;
+}
+
+template <bool ROCKS, bool MULTIROCK, bool CAP, bool NN>
+static void launch_fast(const EuGridDev& g, const EuTablesDev& t, const EuFastDev& f, const EuStepArgs& a,
+                        int slice_lo, int slice_hi, int n_sms, size_t smem, cudaStream_t st)
+{
+    switch (fast_variant()) {
+    case 1:  launch_variant<ROCKS, MULTIROCK, CAP, NN, 3, 4, 5>(g, t, f, a, slice_lo, slice_hi, n_sms, smem, st); break;
+    case 2:  launch_variant<ROCKS, MULTIROCK, CAP, NN, 2, 2, 5>(g, t, f, a, slice_lo, slice_hi, n_sms, smem, st); break;
+    case 3:  launch_variant<ROCKS, MULTIROCK, CAP, NN, 2, 2, 6>(g, t, f, a, slice_lo, slice_hi, n_sms, smem, st); break;
+    case 4:  launch_variant<ROCKS, MULTIROCK, CAP, NN, 1, 1, 6>(g, t, f, a, slice_lo, slice_hi, n_sms, smem, st); break;
+    case 5:  launch_variant<ROCKS, MULTIROCK, CAP, NN, 1, 1, 8>(g, t, f, a, slice_lo, slice_hi, n_sms, smem, st); break;
+    default: launch_variant<ROCKS, MULTIROCK, CAP, NN, 3, 4, 4>(g, t, f, a, slice_lo, slice_hi, n_sms, smem, st); break;
+    }
 }
 
 template <bool ROCKS, bool MULTIROCK>
