@@ -1,0 +1,21 @@
+"""Runs oracle/_ref/dropin_test: the reference Opm::EulerUpstream and the drop-in Opm::b200::EulerUpstream
+(opm-porsol_b200/host) side by side in one C++ program, same GridInterface / ReservoirProperties /
+BoundaryConditions objects (tests/cpp/dropin_test.cpp).  The binary is built where /root/reference exists."""
+import os
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+
+BIN = os.path.join(ROOT, "oracle", "_ref", "dropin_test")
+
+
+@pytest.mark.gpu
+def test_dropin_header_matches_reference(tmp_path):
+    if not os.path.exists(BIN):
+        pytest.skip("oracle/_ref/dropin_test not built (needs /root/reference)")
+    out = subprocess.run([BIN, str(tmp_path)], capture_output=True, text=True, timeout=600)
+    print(out.stdout)
+    print(out.stderr)
+    assert out.returncode == 0 and "DROPIN TEST PASSED" in out.stdout, out.stdout + out.stderr

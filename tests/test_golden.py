@@ -1,0 +1,72 @@
+"""Golden vectors generated from the reference itself (tests/golden/make_golden.py; the reference ships
+none for this path).  CPU: the C oracle reproduces them bit for bit.  GPU: STRICT mode
+reproduces them bit for bit, FAST mode within 1e-12 per substep / 1e-9 per transportSolve."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, small_cases, tensor_cases
+
+ALL = small_cases() + tensor_cases()
+
+
+def golden(name):
+    return np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+
+
+@pytest.mark.parametrize("name,case", ALL, ids=[n for n, _ in ALL])
+def test_oracle_reproduces_golden(name, case):
+    from oracle.ref import PortSolver
+    g = golden(name)
+    chk = np.array([case.sat0.sum(), case.hf_flux.sum(), case.perm.sum(), case.hf_area.sum()])
+    assert np.array_equal(chk, g["input_checksum"]), "seeded inputs differ from the ones the fixture was made with"
+    port = PortSolver(case, cfl_factors=g["cfl_factors"])
+    if case.mobility_kind == 0:
+        assert np.array_equal(port.compute_cfl_factors(), g["cfl_factors"])
+    assert np.array_equal(port.cfl_times(), g["cfl_times"])
+    s = case.sat0.copy()
+    for q in range(3):
+        o = port.small_step(s, float(g["dt"]))
+        s = o["sat"]
+        assert np.array_equal(o["residual"], g["step_res"][q])
+        assert np.array_equal(s, g["step_sat"][q])
+    if case.mobility_kind == 0:
+        sol = port.transport_solve(case.sat0, time=float(g["solve_time"]))
+        assert sol["nsteps"] == int(g["solve_nsteps"]) and sol["attempts"] == int(g["solve_attempts"])
+        assert np.array_equal(sol["sat"], g["solve_sat"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["strict", "fast"])
+@pytest.mark.parametrize("name,case", ALL, ids=[n for n, _ in ALL])
+def test_cuda_reproduces_golden(name, case, mode):
+    from opm_porsol_b200 import EulerUpstream
+    from opm_porsol_b200.binding import params_from_case
+    if case.mobility_kind == 1 and mode == "fast":
+        pytest.skip("tensor mobility runs the STRICT kernels")
+    g = golden(name)
+    dev = EulerUpstream(device=0, mode=mode)
+    dev.init(params_from_case(case))
+    dev.initObj(case, cfl_factors=g["cfl_factors"])
+    dev.upload_state(case.sat0, case.hf_flux)
+    assert np.array_equal(dev.cfl_times(case.gravity), g["cfl_times"])
+    inj = (case.src_cell, case.src_rate)
+    for q in range(3):
+        o = dev.small_step(float(g["dt"]), case.gravity, inj)
+        s = dev.download_saturation()
+        if mode == "strict":
+            assert np.array_equal(o["residual"], g["step_res"][q])
+            assert np.array_equal(s, g["step_sat"][q])
+        else:
+            assert np.abs(s - g["step_sat"][q]).max() <= 1e-12
+        dev.upload_saturation(g["step_sat"][q])
+    if case.mobility_kind == 0:
+        sat = case.sat0.copy()
+        rep = dev.transportSolve(sat, float(g["solve_time"]), case.gravity, case.hf_flux, inj)
+        assert rep.nsteps == int(g["solve_nsteps"]) and rep.attempts == int(g["solve_attempts"])
+        if mode == "strict":
+            assert np.array_equal(sat, g["solve_sat"])
+        else:
+            assert np.abs(sat - g["solve_sat"]).max() <= 1e-9
+    dev.close()
