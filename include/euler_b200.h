@@ -197,15 +197,24 @@ int eu_small_step(eu_handle h, double dt, const double gravity[3],
                   double* residual_out, int* bad_cell, double* bad_value);
 
 /* ---- multi-GPU plumbing (one process per GPU; see DESIGN.md "Multi-GPU") ----------------
- * Ghost saturations travel as peer-to-peer stores over NVLink into buffers exported with CUDA
- * IPC.  The host application only has to all-gather two opaque blobs between the ranks. */
-int eu_comm_blob_size(eu_handle h);                         /* bytes of this rank's blob */
-int eu_comm_export(eu_handle h, void* blob);                /* fill this rank's blob */
-int eu_comm_connect(eu_handle h, const void* all_blobs);    /* world_size blobs, rank order */
-/* host-side reductions the caller performs between ranks (min over ranks of each entry /
- * max over ranks): installed as callbacks so the library stays free of MPI/NCCL. */
+ * Each rank owns a contiguous range of global cells (z-slab) and holds the remote cells its faces touch
+ * as ghost cells.  After every substep the new saturations (and, in FAST mode, capillary pressures) of
+ * the cells a neighbour holds as ghosts are written straight into that neighbour's HBM with
+ * peer-to-peer stores over NVLink (buffers exported with CUDA IPC), followed by an epoch flag; the
+ * neighbour's next substep waits for the flag on its own stream.  Nothing goes through the host.
+ * The host application only has to all-gather one opaque, variable-size blob per rank (eu_comm_export)
+ * and hand all of them to eu_comm_connect, and to provide a tiny min/max reduction for the CFL times
+ * and the range-check flag.  The library itself stays free of MPI/NCCL. */
+int eu_comm_blob_size(eu_handle h);                          /* bytes of this rank's blob (after eu_grid_end) */
+int eu_comm_export(eu_handle h, void* blob);                 /* fill this rank's blob */
+int eu_comm_connect(eu_handle h, int n_blobs, const void* const* blobs, const int* blob_sizes);  /* rank order */
 typedef void (*eu_allreduce_fn)(void* user, double* values, int n, int op /*0 = min, 1 = max*/);
 int eu_comm_set_allreduce(eu_handle h, eu_allreduce_fn fn, void* user);
+/* Pure host logic behind eu_comm_connect, exposed for tests: which of the cells in [own_begin, own_end)
+ * does a peer hold as ghosts?  ghost_global ascending.  Writes, for every match, the global cell id and
+ * the peer's local slot; returns the number of matches. */
+int eu_comm_plan_sends(int own_begin, int own_end, int n_ghost, const int* ghost_global, const int* ghost_local,
+                       int* send_global, int* send_peer_local);
 
 /* ---- host-side helper, no device needed: ReservoirPropertyCapillary<3>::computeCflFactors
  *      (ReservoirPropertyCapillary_impl.hpp:190-281) for callers without the reference's

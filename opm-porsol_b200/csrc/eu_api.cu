@@ -104,9 +104,27 @@ struct eu_solver {
     bool cfl_cap_valid = false, cfl_grav_valid = false;
     double cfl_cap = 1e100, cfl_grav = 1e100, cfl_grav_gravity[3] = { 0, 0, 0 };
     cudaEvent_t ev0, ev1;
-    // comm
+    // comm (one process per GPU): ghost saturations are pushed into the neighbours' buffers
     eu_allreduce_fn allreduce = nullptr;
     void* allreduce_user = nullptr;
+    struct Peer {
+        int rank = -1;
+        bool recv = false;                 // this peer pushes into my ghosts
+        int n_send = 0;
+        double* S[2] = { nullptr, nullptr };
+        double* pc[2] = { nullptr, nullptr };
+        unsigned* flags = nullptr;         // the peer's flag array (I write entry [my rank])
+        void* opened[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
+        DevBuf<int> src, dst;
+        DevBuf<unsigned> counter;
+    };
+    std::vector<Peer*> peers;
+    DevBuf<unsigned> d_comm_flags;         // [world_size], written by the peers
+    DevBuf<int> d_wait_ranks;
+    int n_wait = 0;
+    unsigned epoch = 0;
+    bool comm_ready = false;
+    std::vector<int> ghost_global, ghost_local;
 
     EuGridDev grid() const
     {
@@ -291,6 +309,27 @@ int launch_substep(eu_handle h, const EuStepArgs& a)
     return launches;
 }
 
+// after a substep wrote buffer `out_buf`: push my boundary cells to the peers' ghosts, then make the
+// stream wait for the peers' pushes of the same epoch
+int halo_exchange(eu_handle h, int out_buf, bool with_pc, int* launches)
+{
+    if (h->cfg.world_size <= 1) return EU_OK;
+    if (!h->comm_ready) return fail(h, EU_ERR_COMM, "world_size > 1 needs eu_comm_connect");
+    ++h->epoch;
+    for (eu_solver::Peer* p : h->peers) {
+        if (p->n_send == 0) continue;
+        eu_launch_halo_push(p->src.p, p->dst.p, p->n_send, h->d_S[out_buf].p, p->S[out_buf],
+                            with_pc ? h->d_pc[out_buf].p : nullptr, with_pc ? p->pc[out_buf] : nullptr,
+                            p->counter.p, p->flags + h->cfg.rank, h->epoch, h->st);
+        ++*launches;
+    }
+    if (h->n_wait > 0) {
+        eu_launch_halo_wait(h->d_comm_flags.p, h->d_wait_ranks.p, h->n_wait, h->epoch, 20000000000LL, h->d_flags.p + 3, h->st);
+        ++*launches;
+    }
+    return EU_OK;
+}
+
 int compute_cfl(eu_handle h, const double gravity[3], bool want_v, bool want_g, bool want_c, double out[3],
                 int* zero_flag, int* launches)
 {
@@ -400,6 +439,10 @@ void eu_destroy(eu_handle h)
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     cudaStreamSynchronize(h->st);
+    for (eu_solver::Peer* p : h->peers) {
+        for (void* o : p->opened) if (o) cudaIpcCloseMemHandle(o);
+        delete p;
+    }
     cudaEventDestroy(h->ev0);
     cudaEventDestroy(h->ev1);
     cudaStreamDestroy(h->st);
@@ -752,6 +795,7 @@ int eu_upload_state(eu_handle h, const double* saturation, const double* hf_flux
     if (!h || !hf_flux) return EU_ERR_ARG;
     if (!h->grid_ready) return fail(h, EU_ERR_ARG, "grid not ready");
     EU_CUDA(h, cudaSetDevice(h->cfg.device));
+    h->cur = 0;                                  // every rank keeps the same buffer parity
     EU_CUDA(h, cudaMemcpyAsync(h->d_hf_flux.p, hf_flux, size_t(h->H)*sizeof(double), cudaMemcpyHostToDevice, h->st));
     if (saturation)
         EU_CUDA(h, cudaMemcpyAsync(h->d_S[h->cur].p, saturation, size_t(h->n_local)*sizeof(double), cudaMemcpyHostToDevice, h->st));
@@ -883,13 +927,17 @@ int eu_transport_solve_resident(eu_handle h, double time, const double gravity[3
         for (int q = 0; q < nsteps; ++q) {
             EuStepArgs a = step_args(h, dt, gravity, nls, q);
             launches += launch_substep(h, a);
+            if ((rc = halo_exchange(h, h->cur ^ 1, h->mode == EU_MODE_FAST && p.method_capillary, &launches))) return rc;
             h->cur ^= 1;
         }
         EU_CUDA(h, cudaEventRecord(h->ev1, h->st));
         unsigned long long key = none;
+        int comm_err = 0;
         EU_CUDA(h, cudaMemcpyAsync(&key, h->d_fail_key.p, sizeof(key), cudaMemcpyDeviceToHost, h->st));
+        EU_CUDA(h, cudaMemcpyAsync(&comm_err, h->d_flags.p + 3, sizeof(int), cudaMemcpyDeviceToHost, h->st));
         EU_CUDA(h, cudaStreamSynchronize(h->st));
         EU_CUDA(h, cudaGetLastError());
+        if (comm_err) return fail(h, EU_ERR_COMM, "halo exchange timed out waiting for a neighbour rank");
         rep->substeps_executed += nsteps;
         float ms = 0.f;
         cudaEventElapsedTime(&ms, h->ev0, h->ev1);
@@ -950,9 +998,126 @@ int eu_transport_solve(eu_handle h, double* saturation, double time, const doubl
     return rc != EU_OK ? rc : rc2;
 }
 
-int eu_comm_blob_size(eu_handle h) { (void)h; return 0; }
-int eu_comm_export(eu_handle h, void* blob) { (void)blob; return fail(h, EU_ERR_UNSUPPORTED, "multi-GPU exchange not built yet"); }
-int eu_comm_connect(eu_handle h, const void* all_blobs) { (void)all_blobs; return fail(h, EU_ERR_UNSUPPORTED, "multi-GPU exchange not built yet"); }
+struct EuBlobHeader {
+    int magic, rank, world, own_begin, own_end, n_ghost;
+    cudaIpcMemHandle_t mem[5];       // S[0], S[1], pc[0], pc[1], flags
+};
+
+int eu_comm_plan_sends(int own_begin, int own_end, int n_ghost, const int* ghost_global, const int* ghost_local,
+                       int* send_global, int* send_peer_local)
+{
+    int n = 0;
+    for (int i = 0; i < n_ghost; ++i) {
+        if (ghost_global[i] >= own_begin && ghost_global[i] < own_end) {
+            if (send_global) send_global[n] = ghost_global[i];
+            if (send_peer_local) send_peer_local[n] = ghost_local[i];
+            ++n;
+        }
+    }
+    return n;
+}
+
+static void collect_ghosts(eu_handle h)
+{
+    h->ghost_global.clear();
+    h->ghost_local.clear();
+    for (int l = 0; l < h->n_local; ++l) {
+        if (l >= h->own_lo && l < h->own_hi) { l = h->own_hi - 1; continue; }
+        h->ghost_global.push_back(h->local_to_global(l));
+        h->ghost_local.push_back(l);
+    }
+}
+
+int eu_comm_blob_size(eu_handle h)
+{
+    if (!h || !h->grid_ready) return 0;
+    collect_ghosts(h);
+    return int(sizeof(EuBlobHeader) + 2*sizeof(int)*h->ghost_global.size());
+}
+
+int eu_comm_export(eu_handle h, void* blob)
+{
+    if (!h || !blob) return EU_ERR_ARG;
+    if (!h->grid_ready) return fail(h, EU_ERR_ARG, "eu_comm_export before eu_grid_end");
+    EU_CUDA(h, cudaSetDevice(h->cfg.device));
+    collect_ghosts(h);
+    if (h->d_comm_flags.n == 0) {
+        EU_CUDA(h, h->d_comm_flags.alloc(size_t(std::max(h->cfg.world_size, 1))));
+        EU_CUDA(h, cudaMemset(h->d_comm_flags.p, 0, h->d_comm_flags.n*sizeof(unsigned)));
+    }
+    EuBlobHeader hd;
+    std::memset(&hd, 0, sizeof(hd));
+    hd.magic = 0x45553031; hd.rank = h->cfg.rank; hd.world = h->cfg.world_size;
+    hd.own_begin = h->cfg.own_begin; hd.own_end = h->cfg.own_end; hd.n_ghost = int(h->ghost_global.size());
+    void* ptrs[5] = { h->d_S[0].p, h->d_S[1].p, h->d_pc[0].p, h->d_pc[1].p, h->d_comm_flags.p };
+    for (int k = 0; k < 5; ++k) EU_CUDA(h, cudaIpcGetMemHandle(&hd.mem[k], ptrs[k]));
+    char* out = static_cast<char*>(blob);
+    std::memcpy(out, &hd, sizeof(hd));
+    std::memcpy(out + sizeof(hd), h->ghost_global.data(), sizeof(int)*h->ghost_global.size());
+    std::memcpy(out + sizeof(hd) + sizeof(int)*h->ghost_global.size(), h->ghost_local.data(), sizeof(int)*h->ghost_local.size());
+    return EU_OK;
+}
+
+int eu_comm_connect(eu_handle h, int n_blobs, const void* const* blobs, const int* blob_sizes)
+{
+    if (!h || !blobs || !blob_sizes) return EU_ERR_ARG;
+    if (n_blobs != h->cfg.world_size) return fail(h, EU_ERR_ARG, "one blob per rank expected");
+    if (h->d_comm_flags.n == 0) return fail(h, EU_ERR_ARG, "eu_comm_export must precede eu_comm_connect");
+    EU_CUDA(h, cudaSetDevice(h->cfg.device));
+    for (eu_solver::Peer* p : h->peers) {
+        for (void* o : p->opened) if (o) cudaIpcCloseMemHandle(o);
+        delete p;
+    }
+    h->peers.clear();
+    std::vector<int> wait_ranks;
+    for (int r = 0; r < n_blobs; ++r) {
+        if (r == h->cfg.rank) continue;
+        if (blob_sizes[r] < int(sizeof(EuBlobHeader))) return fail(h, EU_ERR_ARG, "short blob");
+        EuBlobHeader hd;
+        std::memcpy(&hd, blobs[r], sizeof(hd));
+        if (hd.magic != 0x45553031 || hd.rank != r || hd.world != n_blobs) return fail(h, EU_ERR_ARG, "bad blob");
+        if (blob_sizes[r] != int(sizeof(hd) + 2*sizeof(int)*size_t(hd.n_ghost))) return fail(h, EU_ERR_ARG, "blob size mismatch");
+        const int* gg = reinterpret_cast<const int*>(static_cast<const char*>(blobs[r]) + sizeof(hd));
+        const int* gl = gg + hd.n_ghost;
+        std::vector<int> sg(static_cast<size_t>(std::max(hd.n_ghost, 1)), 0), sl(static_cast<size_t>(std::max(hd.n_ghost, 1)), 0);
+        const int n_send = eu_comm_plan_sends(h->cfg.own_begin, h->cfg.own_end, hd.n_ghost, gg, gl, sg.data(), sl.data());
+        bool recv = false;
+        for (int g : h->ghost_global) if (g >= hd.own_begin && g < hd.own_end) { recv = true; break; }
+        if (n_send == 0 && !recv) continue;
+        eu_solver::Peer* p = new eu_solver::Peer;
+        h->peers.push_back(p);
+        p->rank = r; p->recv = recv; p->n_send = n_send;
+        for (int k = 0; k < 5; ++k) {
+            cudaError_t e = cudaIpcOpenMemHandle(&p->opened[k], hd.mem[k], cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess)
+                return fail(h, EU_ERR_COMM, std::string("cudaIpcOpenMemHandle (peer-to-peer access to the neighbour rank): ") + cudaGetErrorString(e));
+        }
+        p->S[0] = static_cast<double*>(p->opened[0]); p->S[1] = static_cast<double*>(p->opened[1]);
+        p->pc[0] = static_cast<double*>(p->opened[2]); p->pc[1] = static_cast<double*>(p->opened[3]);
+        p->flags = static_cast<unsigned*>(p->opened[4]);
+        if (n_send > 0) {
+            std::vector<int> src(static_cast<size_t>(n_send), 0);
+            std::vector<int> dst(sl.begin(), sl.begin() + n_send);
+            for (int i = 0; i < n_send; ++i) src[size_t(i)] = h->global_to_local(sg[size_t(i)]);
+            int rc;
+            if ((rc = upload_vec(h, p->src, src))) return rc;
+            if ((rc = upload_vec(h, p->dst, dst))) return rc;
+            EU_CUDA(h, p->counter.alloc(1));
+            EU_CUDA(h, cudaMemset(p->counter.p, 0, sizeof(unsigned)));
+        }
+        if (recv) wait_ranks.push_back(r);
+    }
+    if (wait_ranks.size() > 32) return fail(h, EU_ERR_UNSUPPORTED, "more than 32 neighbour ranks");
+    h->n_wait = int(wait_ranks.size());
+    if (h->n_wait > 0) {
+        int rc;
+        if ((rc = upload_vec(h, h->d_wait_ranks, wait_ranks))) return rc;
+    }
+    h->epoch = 0;
+    h->comm_ready = true;
+    return EU_OK;
+}
+
 int eu_comm_set_allreduce(eu_handle h, eu_allreduce_fn fn, void* user)
 {
     if (!h) return EU_ERR_ARG;

@@ -140,6 +140,12 @@ int eu_cfl_blocks(int n_cells);
 void eu_launch_strict_pc(const EuGridDev& g, const EuTablesDev& t, const double* S, double* pc, cudaStream_t st);
 void eu_launch_strict_step(const EuGridDev& g, const EuTablesDev& t, const EuStrictDev& s, const double* hf_flux,
                            const EuStepArgs& a, cudaStream_t st);
+// halo exchange (eu_setup.cu): peer-to-peer stores + epoch flags
+void eu_launch_halo_push(const int* send_src, const int* send_dst, int n, const double* S_local, double* S_peer,
+                         const double* pc_local, double* pc_peer, unsigned* block_counter, unsigned* peer_flag,
+                         unsigned epoch, cudaStream_t st);
+void eu_launch_halo_wait(const unsigned* my_flags, const int* wait_ranks, int n_wait, unsigned epoch,
+                         long long timeout_cycles, int* err_flag, cudaStream_t st);
 // ---- eu_fast.cu ------------------------------------------------------------------------------
 void eu_launch_fast_pc(const EuGridDev& g, const EuTablesDev& t, const EuFastDev& f, const double* S, double* pc,
                        int lo, int hi, cudaStream_t st);

@@ -580,6 +580,47 @@ __global__ void __launch_bounds__(128) k_strict_step(EuGridDev g, EuTablesDev t,
     a.S_out[c] = sat;
 }
 
+// ---------------------------------------------------------------------------------------
+// Halo exchange.  The cells a neighbour rank holds as ghosts are written into ITS saturation buffer
+// with plain stores through a peer mapping (NVLink P2P); the last block to finish publishes the epoch in
+// the neighbour's flag word.  The neighbour spins on its own flag word before its next substep.
+// ---------------------------------------------------------------------------------------
+__global__ void k_halo_push(const int* __restrict__ send_src, const int* __restrict__ send_dst, int n,
+                            const double* __restrict__ S_local, double* __restrict__ S_peer,
+                            const double* __restrict__ pc_local, double* __restrict__ pc_peer,
+                            unsigned* __restrict__ block_counter, unsigned* peer_flag, unsigned epoch)
+{
+    for (int i = blockIdx.x*blockDim.x + threadIdx.x; i < n; i += gridDim.x*blockDim.x) {
+        const int s = send_src[i], d = send_dst[i];
+        S_peer[d] = S_local[s];
+        if (pc_peer) pc_peer[d] = pc_local[s];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned done = atomicAdd(block_counter, 1u);
+        if (done == gridDim.x - 1) {
+            *block_counter = 0;
+            __threadfence_system();
+            *(volatile unsigned*)peer_flag = epoch;
+            __threadfence_system();
+        }
+    }
+}
+
+__global__ void k_halo_wait(const unsigned* my_flags, const int* __restrict__ wait_ranks, int n_wait, unsigned epoch,
+                            long long timeout_cycles, int* err_flag)
+{
+    if (threadIdx.x >= n_wait) return;
+    const volatile unsigned* f = my_flags + wait_ranks[threadIdx.x];
+    const long long t0 = clock64();
+    while ((int)(*f - epoch) < 0) {
+        __nanosleep(200);
+        if (clock64() - t0 > timeout_cycles) { atomicExch(err_flag, 1); break; }   // never hang the GPU
+    }
+    __threadfence_system();
+}
+
 } // namespace
 
 // ---------------------------------------------------------------------------------------
@@ -663,4 +704,20 @@ void eu_launch_strict_step(const EuGridDev& g, const EuTablesDev& t, const EuStr
     if (n <= 0) return;
     if (t.kind == EU_MOB_SCALAR) k_strict_step<0><<<div_up(n, 128), 128, 0, st>>>(g, t, s, hf_flux, a);
     else                         k_strict_step<1><<<div_up(n, 128), 128, 0, st>>>(g, t, s, hf_flux, a);
+}
+
+void eu_launch_halo_push(const int* send_src, const int* send_dst, int n, const double* S_local, double* S_peer,
+                         const double* pc_local, double* pc_peer, unsigned* block_counter, unsigned* peer_flag,
+                         unsigned epoch, cudaStream_t st)
+{
+    int blocks = div_up(n > 0 ? n : 1, kThreads);
+    if (blocks > 64) blocks = 64;
+    k_halo_push<<<blocks, kThreads, 0, st>>>(send_src, send_dst, n, S_local, S_peer, pc_local, pc_peer, block_counter,
+                                             peer_flag, epoch);
+}
+void eu_launch_halo_wait(const unsigned* my_flags, const int* wait_ranks, int n_wait, unsigned epoch,
+                         long long timeout_cycles, int* err_flag, cudaStream_t st)
+{
+    if (n_wait <= 0) return;
+    k_halo_wait<<<1, 32, 0, st>>>(my_flags, wait_ranks, n_wait, epoch, timeout_cycles, err_flag);
 }

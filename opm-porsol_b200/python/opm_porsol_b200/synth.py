@@ -574,3 +574,91 @@ def c4_fluid_case(capillary=False):
     return make_case("C4-fluid", g, poro=np.full(1, 0.2), perm=perm, rock_id=np.zeros(1, dtype=np.int32),
                      rocks=[corey_table()], sat0=np.zeros(1), gravity=[0.0, 0.0, -9.80665],
                      hf_flux=np.zeros(6), method_capillary=capillary)
+
+
+# ----------------------------------------------------------------------------------
+# Decomposition helpers: the part of a (small, fully materialised) Case that one rank of an
+# index-range (z-slab) decomposition uploads -- own cells plus the ghost cells its faces touch.
+# ----------------------------------------------------------------------------------
+def extract_slab(case, own_begin, own_end):
+    """Returns dict(cells, hf_index, chunks, n_local, n_hf): ``cells`` = ascending global ids of the local
+    (own + ghost) cells, ``hf_index`` = global half-face indices of their half-faces (so that
+    sat_local = sat[cells], flux_local = hf_flux[hf_index]) and ``chunks`` in eu_grid_chunk layout."""
+    from .binding import resolve_boundary
+    off = case.hf_offset.astype(np.int64)
+    own = np.arange(own_begin, own_end)
+    bnd_hf, kind, sat, pcell, pface = resolve_boundary(case)
+    h0, h1 = off[own_begin], off[own_end]
+    nb = case.hf_nbr[h0:h1].astype(np.int64)
+    touched = [nb[nb >= 0]]
+    b0, b1 = np.searchsorted(bnd_hf, [h0, h1])
+    pc = pcell[b0:b1]
+    touched.append(pc[pc >= 0].astype(np.int64))
+    cells = np.union1d(own, np.concatenate(touched))
+    counts = (off[cells + 1] - off[cells]).astype(np.int64)
+    hf_index = np.concatenate([np.arange(off[c], off[c + 1]) for c in cells]) if cells.size else np.zeros(0, np.int64)
+    # contiguous runs of cells -> chunks
+    breaks = np.nonzero(np.diff(cells) != 1)[0] + 1
+    starts = np.concatenate([[0], breaks])
+    ends = np.concatenate([breaks, [cells.size]])
+    hf_starts = np.concatenate([[0], np.cumsum(counts)])
+    chunks = []
+    for a, b in zip(starts, ends):
+        c0, c1 = int(cells[a]), int(cells[b - 1]) + 1
+        g0, g1 = int(off[c0]), int(off[c1])
+        k0, k1 = np.searchsorted(bnd_hf, [g0, g1])
+        chunks.append(dict(
+            first_cell=c0, n_cells=c1 - c0,
+            hf_count=_i32(off[c0 + 1:c1 + 1] - off[c0:c1]), hf_neighbour=_i32(case.hf_nbr[g0:g1]),
+            hf_area=_f64(case.hf_area[g0:g1]), hf_normal=_f64(case.hf_normal[g0:g1]), hf_centroid=_f64(case.hf_centroid[g0:g1]),
+            bnd_hf=_i32(bnd_hf[k0:k1] - g0), bnd_kind=_i32(kind[k0:k1]), bnd_sat=_f64(sat[k0:k1]),
+            bnd_partner_cell=_i32(pcell[k0:k1]), bnd_partner_face=_i32(pface[k0:k1]),
+            cell_volume=_f64(case.cell_volume[c0:c1]), cell_centroid=_f64(case.cell_centroid[c0:c1]),
+            porosity=_f64(case.poro[c0:c1]), permeability=_f64(case.perm[c0:c1]),
+            rock_id=_i32(case.rock_id[c0:c1]) if case.rock_id is not None else None))
+    return dict(cells=cells, hf_index=hf_index, chunks=chunks, n_local=int(cells.size), n_hf=int(hf_index.size),
+                own_begin=own_begin, own_end=own_end, hf_starts=hf_starts)
+
+
+def local_case(case, slab):
+    """A self-contained Case over the local cells of ``slab`` (local numbering), for running the CPU oracle
+    on one rank's part: neighbours that are not local become dummy Dirichlet boundary faces (they only
+    occur on ghost cells, whose results are discarded)."""
+    import copy
+    cells = slab["cells"]
+    hfi = slab["hf_index"]
+    g2l = np.full(case.N, -1, dtype=np.int64)
+    g2l[cells] = np.arange(cells.size)
+    nbr_g = case.hf_nbr[hfi].astype(np.int64)
+    nbr_l = np.where(nbr_g >= 0, g2l[np.maximum(nbr_g, 0)], -1)
+    bid = case.hf_bid[hfi].astype(np.int64).copy()
+    n_bid = case.bid_kind.shape[0]
+    missing = (nbr_g >= 0) & (nbr_l < 0)
+    bid[missing] = n_bid                               # dummy Dirichlet id
+    # periodic faces of ghost cells whose partner cell is not local -> dummy as well
+    from .binding import resolve_boundary
+    bnd_hf, kind, sat, pcell, pface = resolve_boundary(case)
+    pc_of_hf = np.full(case.H, -2, dtype=np.int64)
+    pc_of_hf[bnd_hf] = pcell
+    p = pc_of_hf[hfi]
+    lost = (p >= 0) & (g2l[np.maximum(p, 0)] < 0)
+    bid[lost] = n_bid
+    c = copy.copy(case)
+    c.N = int(cells.size)
+    c.hf_offset = _i32(slab["hf_starts"])
+    c.hf_nbr = _i32(nbr_l)
+    c.hf_bid = _i32(bid)
+    c.hf_area, c.hf_normal, c.hf_centroid = _f64(case.hf_area[hfi]), _f64(case.hf_normal[hfi]), _f64(case.hf_centroid[hfi])
+    c.cell_volume, c.cell_centroid = _f64(case.cell_volume[cells]), _f64(case.cell_centroid[cells])
+    c.poro, c.perm = _f64(case.poro[cells]), _f64(case.perm[cells])
+    c.rock_id = _i32(case.rock_id[cells]) if case.rock_id is not None else None
+    c.bid_kind = _i32(np.concatenate([case.bid_kind, [0]]))
+    c.bid_sat = _f64(np.concatenate([case.bid_sat, [0.5]]))
+    c.bid_partner = _i32(np.concatenate([case.bid_partner, [0]]))
+    c.sat0 = _f64(case.sat0[cells])
+    c.hf_flux = _f64(case.hf_flux[hfi])
+    own = (cells >= slab["own_begin"]) & (cells < slab["own_end"])
+    keep = np.isin(case.src_cell, cells[own])
+    c.src_cell = _i32(g2l[case.src_cell[keep]])
+    c.src_rate = _f64(case.src_rate[keep])
+    return c
