@@ -119,6 +119,13 @@ struct eu_solver {
         DevBuf<unsigned> counter;
     };
     std::vector<Peer*> peers;
+    // fused exchange (FAST mode): boundary slice ranges at the two ends of the own range
+    bool fused_ok = false;
+    int fused_a_hi = 0, fused_b_lo = 0;
+    int fused_peer[2] = { -1, -1 };        // index into peers
+    unsigned fused_total[2] = { 0, 0 };
+    DevBuf<int> d_fused_dst[2];
+    DevBuf<unsigned> d_fused_dummy;
     DevBuf<unsigned> d_comm_flags;         // [world_size], written by the peers
     DevBuf<int> d_wait_ranks;
     int n_wait = 0;
@@ -287,14 +294,48 @@ EuStepArgs step_args(eu_handle h, double dt, const double gravity[3], int n_src,
     return a;
 }
 
-// one substep on the resident state; returns the number of kernels launched
-int launch_substep(eu_handle h, const EuStepArgs& a)
+bool fused_halo(eu_handle h)
+{
+    return h->cfg.world_size > 1 && h->comm_ready && h->mode == EU_MODE_FAST && h->fused_ok;
+}
+
+// one substep on the resident state; returns the number of kernels launched.  In FAST mode with several
+// ranks the halo exchange is part of the kernel (`exchange`: this substep takes part in the lockstep).
+int launch_substep(eu_handle h, const EuStepArgs& a, bool exchange)
 {
     const EuGridDev g = h->grid();
     if (h->mode == EU_MODE_FAST) {
         const int slice_lo = h->own_lo/EU_SLICE;
         const int slice_hi = (h->own_hi + EU_SLICE - 1)/EU_SLICE;
-        eu_launch_fast_step(g, h->tab, h->fast(), a, slice_lo, slice_hi, h->n_sms, h->st);
+        EuHaloDev halo;
+        std::memset(&halo, 0, sizeof(halo));
+        if (exchange && fused_halo(h)) {
+            const int out = h->cur ^ 1;
+            halo.enabled = 1;
+            halo.a_hi = h->fused_a_hi;
+            halo.b_lo = h->fused_b_lo;
+            halo.epoch = ++h->epoch;
+            for (int r = 0; r < 2; ++r) {
+                halo.dst[r] = h->d_fused_dst[r].p;
+                if (h->fused_peer[r] >= 0) {
+                    eu_solver::Peer* p = h->peers[size_t(h->fused_peer[r])];
+                    halo.peer_S[r] = p->S[out];
+                    halo.peer_pc[r] = a.method_capillary ? p->pc[out] : nullptr;
+                    halo.counter[r] = p->counter.p;
+                    halo.peer_flag[r] = p->flags + h->cfg.rank;
+                } else {
+                    halo.counter[r] = h->d_fused_dummy.p;
+                    halo.peer_flag[r] = h->d_fused_dummy.p + 1;
+                }
+                halo.total[r] = h->fused_total[r];
+            }
+            halo.my_flags = h->d_comm_flags.p;
+            halo.n_wait = 0;
+            for (eu_solver::Peer* p : h->peers) if (p->recv && halo.n_wait < 2) halo.wait_rank[halo.n_wait++] = p->rank;
+            halo.timeout_cycles = 20000000000LL;
+            halo.err_flag = h->d_flags.p + 3;
+        }
+        eu_launch_fast_step(g, h->tab, h->fast(), a, halo, slice_lo, slice_hi, h->n_sms, h->st);
         return 1;
     }
     int launches = 1;
@@ -315,6 +356,7 @@ int halo_exchange(eu_handle h, int out_buf, bool with_pc, int* launches)
 {
     if (h->cfg.world_size <= 1) return EU_OK;
     if (!h->comm_ready) return fail(h, EU_ERR_COMM, "world_size > 1 needs eu_comm_connect");
+    if (fused_halo(h)) return EU_OK;           // done inside k_fast_step
     ++h->epoch;
     for (eu_solver::Peer* p : h->peers) {
         if (p->n_send == 0) continue;
@@ -846,7 +888,8 @@ int eu_small_step(eu_handle h, double dt, const double gravity[3], int n_src, co
     a.residual_out = h->d_residual.p;
     // ghost entries of the new state keep the old values (single substep, no exchange)
     EU_CUDA(h, cudaMemcpyAsync(h->d_S[h->cur ^ 1].p, h->d_S[h->cur].p, size_t(h->n_local)*sizeof(double), cudaMemcpyDeviceToDevice, h->st));
-    launch_substep(h, a);
+    if (h->cfg.world_size > 1) return fail(h, EU_ERR_UNSUPPORTED, "eu_small_step is a single-rank debugging entry point");
+    launch_substep(h, a, false);
     h->cur ^= 1;
     unsigned long long key = none;
     EU_CUDA(h, cudaMemcpyAsync(&key, h->d_fail_key.p, sizeof(key), cudaMemcpyDeviceToHost, h->st));
@@ -879,6 +922,12 @@ int eu_transport_solve_resident(eu_handle h, double time, const double gravity[3
     int rc, nls = 0, launches = 0;
     if ((rc = upload_sources(h, n_src, src_cell, src_rate, &nls))) return rc;
 
+    // saturation_initial (:181) and the second ping-pong buffer.  These copies must be complete on every rank
+    // before any neighbour starts pushing ghosts; the reductions inside compute_cfl are that barrier.
+    const size_t nbytes = size_t(h->n_local)*sizeof(double);
+    EU_CUDA(h, cudaMemcpyAsync(h->d_S_init.p, h->d_S[h->cur].p, nbytes, cudaMemcpyDeviceToDevice, h->st));
+    EU_CUDA(h, cudaMemcpyAsync(h->d_S[h->cur ^ 1].p, h->d_S[h->cur].p, nbytes, cudaMemcpyDeviceToDevice, h->st));
+
     // ---- computeCflTime (EulerUpstream_impl.hpp:263-331)
     int zero = 0;
     double cfl[3];
@@ -906,10 +955,6 @@ int eu_transport_solve_resident(eu_handle h, double time, const double gravity[3
     double dt = time/nsteps;
 
     if ((rc = ensure_contracted(h, gravity))) return rc;
-    const size_t nbytes = size_t(h->n_local)*sizeof(double);
-    EU_CUDA(h, cudaMemcpyAsync(h->d_S_init.p, h->d_S[h->cur].p, nbytes, cudaMemcpyDeviceToDevice, h->st));   // saturation_initial (:181)
-    // ghost entries of the second buffer: single-rank runs have none; multi-rank exchange fills them
-    EU_CUDA(h, cudaMemcpyAsync(h->d_S[h->cur ^ 1].p, h->d_S[h->cur].p, nbytes, cudaMemcpyDeviceToDevice, h->st));
 
     const unsigned long long none = ~0ULL;
     int repeats = 0;
@@ -926,11 +971,16 @@ int eu_transport_solve_resident(eu_handle h, double time, const double gravity[3
         EU_CUDA(h, cudaEventRecord(h->ev0, h->st));
         for (int q = 0; q < nsteps; ++q) {
             EuStepArgs a = step_args(h, dt, gravity, nls, q);
-            launches += launch_substep(h, a);
+            launches += launch_substep(h, a, true);
             if ((rc = halo_exchange(h, h->cur ^ 1, h->mode == EU_MODE_FAST && p.method_capillary, &launches))) return rc;
             h->cur ^= 1;
         }
         EU_CUDA(h, cudaEventRecord(h->ev1, h->st));
+        if (h->cfg.world_size > 1 && h->n_wait > 0) {
+            // the neighbours' last pushes must have landed before anything else touches the ghosts
+            eu_launch_halo_wait(h->d_comm_flags.p, h->d_wait_ranks.p, h->n_wait, h->epoch, 20000000000LL, h->d_flags.p + 3, h->st);
+            ++launches;
+        }
         unsigned long long key = none;
         int comm_err = 0;
         EU_CUDA(h, cudaMemcpyAsync(&key, h->d_fail_key.p, sizeof(key), cudaMemcpyDeviceToHost, h->st));
@@ -972,6 +1022,12 @@ int eu_transport_solve_resident(eu_handle h, double time, const double gravity[3
             dt = time/nsteps;
             EU_CUDA(h, cudaMemcpyAsync(h->d_S[h->cur].p, h->d_S_init.p, nbytes, cudaMemcpyDeviceToDevice, h->st));
             EU_CUDA(h, cudaMemcpyAsync(h->d_S[h->cur ^ 1].p, h->d_S_init.p, nbytes, cudaMemcpyDeviceToDevice, h->st));
+            if (h->cfg.world_size > 1) {
+                // every rank must have restored its buffers before a neighbour pushes into them again
+                EU_CUDA(h, cudaStreamSynchronize(h->st));
+                double dummy = 0.0;
+                h->allreduce(h->allreduce_user, &dummy, 1, 1);
+            }
         }
     }
     rep->nsteps = nsteps;
@@ -1114,6 +1170,69 @@ int eu_comm_connect(eu_handle h, int n_blobs, const void* const* blobs, const in
         if ((rc = upload_vec(h, h->d_wait_ranks, wait_ranks))) return rc;
     }
     h->epoch = 0;
+    // ---- plan of the fused exchange (FAST mode): boundary slice ranges and per-cell ghost slots
+    h->fused_ok = false;
+    if (h->mode == EU_MODE_FAST) {
+        int init[4] = { -1, INT_MAX, 0, 0 };
+        DevBuf<int> d_adj;
+        EU_CUDA(h, d_adj.alloc(4));
+        EU_CUDA(h, cudaMemcpyAsync(d_adj.p, init, sizeof(init), cudaMemcpyHostToDevice, h->st));
+        eu_launch_ghost_adjacent(h->grid(), d_adj.p, h->st);
+        int adj[4];
+        EU_CUDA(h, cudaMemcpyAsync(adj, d_adj.p, sizeof(adj), cudaMemcpyDeviceToHost, h->st));
+        EU_CUDA(h, cudaStreamSynchronize(h->st));
+        int down_max = adj[0], up_min = adj[1];
+        const int mid = h->own_lo + (h->own_hi - h->own_lo)/2;
+        std::vector<std::vector<int> > srcs(h->peers.size()), dsts(h->peers.size());
+        for (size_t k = 0; k < h->peers.size(); ++k) {
+            eu_solver::Peer* p = h->peers[k];
+            if (p->n_send == 0) continue;
+            srcs[k].resize(size_t(p->n_send)); dsts[k].resize(size_t(p->n_send));
+            EU_CUDA(h, cudaMemcpy(srcs[k].data(), p->src.p, sizeof(int)*size_t(p->n_send), cudaMemcpyDeviceToHost));
+            EU_CUDA(h, cudaMemcpy(dsts[k].data(), p->dst.p, sizeof(int)*size_t(p->n_send), cudaMemcpyDeviceToHost));
+            for (int c : srcs[k]) {
+                if (c < mid) down_max = std::max(down_max, c); else up_min = std::min(up_min, c);
+            }
+        }
+        const int slice_lo = h->own_lo/EU_SLICE, slice_hi = (h->own_hi + EU_SLICE - 1)/EU_SLICE;
+        const int a_hi = down_max >= 0 ? down_max/EU_SLICE + 1 : slice_lo;
+        const int b_lo = up_min < INT_MAX ? up_min/EU_SLICE : slice_hi;
+        bool ok = a_hi <= b_lo && h->n_wait <= 2;
+        std::vector<int> dst[2];
+        dst[0].assign(size_t(std::max(1, (a_hi - slice_lo)*EU_SLICE)), -1);
+        dst[1].assign(size_t(std::max(1, (slice_hi - b_lo)*EU_SLICE)), -1);
+        int range_peer[2] = { -1, -1 };
+        for (size_t k = 0; k < h->peers.size() && ok; ++k) {
+            for (size_t i = 0; i < srcs[k].size(); ++i) {
+                const int c = srcs[k][i], sl = c/EU_SLICE;
+                const int r = sl < a_hi ? 0 : (sl >= b_lo ? 1 : -1);
+                if (r < 0 || (range_peer[r] >= 0 && range_peer[r] != int(k))) { ok = false; break; }
+                range_peer[r] = int(k);
+                int& slot = dst[r][size_t(c - (r == 0 ? slice_lo : b_lo)*EU_SLICE)];
+                if (slot >= 0) { ok = false; break; }          // one cell, two ghost slots
+                slot = dsts[k][i];
+            }
+        }
+        if (ok) {
+            int rc;
+            for (int r = 0; r < 2; ++r) if ((rc = upload_vec(h, h->d_fused_dst[r], dst[r]))) return rc;
+            EU_CUDA(h, h->d_fused_dummy.alloc(2));
+            EU_CUDA(h, cudaMemset(h->d_fused_dummy.p, 0, 2*sizeof(unsigned)));
+            const unsigned nA = unsigned(a_hi - slice_lo), nB = unsigned(slice_hi - b_lo);
+            h->fused_a_hi = a_hi; h->fused_b_lo = b_lo;
+            h->fused_peer[0] = range_peer[0]; h->fused_peer[1] = range_peer[1];
+            if (range_peer[0] >= 0 && range_peer[0] == range_peer[1]) {
+                h->fused_total[0] = h->fused_total[1] = nA + nB;       // one neighbour on both sides (periodic, 2 ranks)
+            } else {
+                h->fused_total[0] = range_peer[0] >= 0 ? nA : 0xffffffffu;
+                h->fused_total[1] = range_peer[1] >= 0 ? nB : 0xffffffffu;
+            }
+            // every neighbour that expects pushes must be fed by a range
+            for (size_t k = 0; k < h->peers.size(); ++k)
+                if (h->peers[k]->n_send > 0 && range_peer[0] != int(k) && range_peer[1] != int(k)) ok = false;
+        }
+        h->fused_ok = ok;
+    }
     h->comm_ready = true;
     return EU_OK;
 }

@@ -252,7 +252,7 @@ __device__ double gather_cell_loop(const TabLayout& L, const EuGridDev& g, const
 
 template <bool ROCKS, bool MULTIROCK, bool CAP, bool NN, int B6, int B8, int MINB>
 __global__ void __launch_bounds__(kBlock, MINB) k_fast_step(EuGridDev g, EuTablesDev t, EuFastDev f, EuStepArgs a,
-                                                         int slice_lo, int slice_hi)
+                                                            EuHaloDev halo, int slice_lo, int slice_hi)
 {
     TabLayout L;
     L.nn = t.n_nodes_total; L.nb = t.n_buckets; L.shift = 0;
@@ -260,20 +260,43 @@ __global__ void __launch_bounds__(kBlock, MINB) k_fast_step(EuGridDev g, EuTable
         tables_to_smem(t);
         __syncthreads();
     }
-    {
+    if (!halo.enabled) {   // (with a halo exchange every rank keeps stepping so that the flags stay in lockstep)
         const unsigned long long key = *a.fail_key;
         if (key != ~0ULL && (unsigned)(key >> 32) < (unsigned)a.substep) return;
     }
     const int lane = threadIdx.x & 31;
     const int warp_global = blockIdx.x*kWarpsPerBlock + (threadIdx.x >> 5);
     const int n_warps = gridDim.x*kWarpsPerBlock;
+    // processing order: boundary range A, boundary range B, then the interior
+    const int nA = halo.enabled ? halo.a_hi - slice_lo : 0;
+    const int nB = halo.enabled ? slice_hi - halo.b_lo : 0;
+    bool waited = false;
 
-    for (int s = slice_lo + warp_global; s < slice_hi; s += n_warps) {
+    for (int v = warp_global; v < slice_hi - slice_lo; v += n_warps) {
+        int s, range = -1;
+        if (v < nA)           { s = slice_lo + v; range = 0; }
+        else if (v < nA + nB) { s = halo.b_lo + (v - nA); range = 1; }
+        else                  { s = slice_lo + nA + (v - nA - nB); }
+        if (range >= 0 && !waited) {
+            // ghosts of the previous substep must have landed before a boundary slice reads them
+            if (lane < halo.n_wait) {
+                const volatile unsigned* fl = halo.my_flags + halo.wait_rank[lane];
+                const long long t0 = clock64();
+                while ((int)(*fl - (halo.epoch - 1u)) < 0) {
+                    __nanosleep(100);
+                    if (clock64() - t0 > halo.timeout_cycles) { atomicExch(halo.err_flag, 1); break; }
+                }
+                __threadfence_system();
+            }
+            __syncwarp();
+            waited = true;
+        }
         const int c = s*EU_SLICE + lane;
         const bool active = (c >= g.own_lo) && (c < g.own_hi);
         const int base = f.slice_base[s];
         const int width = (f.slice_base[s + 1] - base) >> 5;
-        if (!active) continue;
+        if (!active && range < 0) continue;
+        if (active) {
         const double S0 = a.S_in[c];
         const int rock0 = MULTIROCK ? f.rock8[c] : 0;
         const double pc0 = CAP ? a.pc_in[c] : 0.0;
@@ -308,7 +331,31 @@ __global__ void __launch_bounds__(kBlock, MINB) k_fast_step(EuGridDev g, EuTable
             }
         }
         a.S_out[c] = sat;
-        if (CAP) a.pc_out[c] = Mob<ROCKS, MULTIROCK>::pc(L, rock0, sat, ROCKS ? f.pcscale[c] : 1.0);
+        double pcn = 0.0;
+        if (CAP) { pcn = Mob<ROCKS, MULTIROCK>::pc(L, rock0, sat, ROCKS ? f.pcscale[c] : 1.0); a.pc_out[c] = pcn; }
+        if (range >= 0) {
+            // this cell is a ghost of the neighbour rank: store it into the neighbour's HBM as well
+            const int first = (range == 0 ? slice_lo : halo.b_lo)*EU_SLICE;
+            const int d = halo.dst[range][c - first];
+            if (d >= 0) {
+                halo.peer_S[range][d] = sat;
+                if (CAP && halo.peer_pc[range]) halo.peer_pc[range][d] = pcn;
+            }
+            __threadfence_system();
+        }
+        }   // active
+        if (range >= 0) {
+            __syncwarp();
+            if (lane == 0) {
+                const unsigned done = atomicAdd(halo.counter[range], 1u);
+                if (done == halo.total[range] - 1u) {
+                    *halo.counter[range] = 0u;
+                    __threadfence_system();
+                    *(volatile unsigned*)halo.peer_flag[range] = halo.epoch;
+                    __threadfence_system();
+                }
+            }
+        }
     }
 }
 
@@ -350,7 +397,7 @@ void eu_launch_fast_pc(const EuGridDev& g, const EuTablesDev& t, const EuFastDev
 
 template <bool ROCKS, bool MULTIROCK, bool CAP, bool NN, int B6, int B8, int MINB>
 static void launch_variant(const EuGridDev& g, const EuTablesDev& t, const EuFastDev& f, const EuStepArgs& a,
-                           int slice_lo, int slice_hi, int n_sms, size_t smem, cudaStream_t st)
+                           const EuHaloDev& halo, int slice_lo, int slice_hi, int n_sms, size_t smem, cudaStream_t st)
 {
     static int blocks_per_sm = 0;
     auto kern = k_fast_step<ROCKS, MULTIROCK, CAP, NN, B6, B8, MINB>;
@@ -364,7 +411,7 @@ static void launch_variant(const EuGridDev& g, const EuTablesDev& t, const EuFas
     int blocks = n_sms*blocks_per_sm;
     const int need = (n + kWarpsPerBlock - 1)/kWarpsPerBlock;
     if (blocks > need) blocks = need;
-    kern<<<blocks, kBlock, smem, st>>>(g, t, f, a, slice_lo, slice_hi);
+    kern<<<blocks, kBlock, smem, st>>>(g, t, f, a, halo, slice_lo, slice_hi);
 }
 
 // EU_FAST_VARIANT (tuning knob, read once): faces per load batch / resident blocks per SM
@@ -377,36 +424,36 @@ static int fast_variant()
 
 template <bool ROCKS, bool MULTIROCK, bool CAP, bool NN>
 static void launch_fast(const EuGridDev& g, const EuTablesDev& t, const EuFastDev& f, const EuStepArgs& a,
-                        int slice_lo, int slice_hi, int n_sms, size_t smem, cudaStream_t st)
+                        const EuHaloDev& halo, int slice_lo, int slice_hi, int n_sms, size_t smem, cudaStream_t st)
 {
     switch (fast_variant()) {
-    case 1:  launch_variant<ROCKS, MULTIROCK, CAP, NN, 3, 4, 5>(g, t, f, a, slice_lo, slice_hi, n_sms, smem, st); break;
-    case 2:  launch_variant<ROCKS, MULTIROCK, CAP, NN, 2, 2, 5>(g, t, f, a, slice_lo, slice_hi, n_sms, smem, st); break;
-    case 3:  launch_variant<ROCKS, MULTIROCK, CAP, NN, 2, 2, 6>(g, t, f, a, slice_lo, slice_hi, n_sms, smem, st); break;
-    case 4:  launch_variant<ROCKS, MULTIROCK, CAP, NN, 1, 1, 6>(g, t, f, a, slice_lo, slice_hi, n_sms, smem, st); break;
-    case 5:  launch_variant<ROCKS, MULTIROCK, CAP, NN, 1, 1, 8>(g, t, f, a, slice_lo, slice_hi, n_sms, smem, st); break;
-    default: launch_variant<ROCKS, MULTIROCK, CAP, NN, 3, 4, 4>(g, t, f, a, slice_lo, slice_hi, n_sms, smem, st); break;
+    case 1:  launch_variant<ROCKS, MULTIROCK, CAP, NN, 3, 4, 5>(g, t, f, a, halo, slice_lo, slice_hi, n_sms, smem, st); break;
+    case 2:  launch_variant<ROCKS, MULTIROCK, CAP, NN, 2, 2, 5>(g, t, f, a, halo, slice_lo, slice_hi, n_sms, smem, st); break;
+    case 3:  launch_variant<ROCKS, MULTIROCK, CAP, NN, 2, 2, 6>(g, t, f, a, halo, slice_lo, slice_hi, n_sms, smem, st); break;
+    case 4:  launch_variant<ROCKS, MULTIROCK, CAP, NN, 1, 1, 6>(g, t, f, a, halo, slice_lo, slice_hi, n_sms, smem, st); break;
+    case 5:  launch_variant<ROCKS, MULTIROCK, CAP, NN, 1, 1, 8>(g, t, f, a, halo, slice_lo, slice_hi, n_sms, smem, st); break;
+    default: launch_variant<ROCKS, MULTIROCK, CAP, NN, 3, 4, 4>(g, t, f, a, halo, slice_lo, slice_hi, n_sms, smem, st); break;
     }
 }
 
 template <bool ROCKS, bool MULTIROCK>
 static void launch_fast2(const EuGridDev& g, const EuTablesDev& t, const EuFastDev& f, const EuStepArgs& a,
-                         int slice_lo, int slice_hi, int n_sms, size_t smem, cudaStream_t st)
+                         const EuHaloDev& halo, int slice_lo, int slice_hi, int n_sms, size_t smem, cudaStream_t st)
 {
     const bool cap = a.method_capillary != 0;
     const bool nn = f.nn != nullptr;
-    if (cap && nn)       launch_fast<ROCKS, MULTIROCK, true, true>(g, t, f, a, slice_lo, slice_hi, n_sms, smem, st);
-    else if (cap)        launch_fast<ROCKS, MULTIROCK, true, false>(g, t, f, a, slice_lo, slice_hi, n_sms, smem, st);
-    else if (nn)         launch_fast<ROCKS, MULTIROCK, false, true>(g, t, f, a, slice_lo, slice_hi, n_sms, smem, st);
-    else                 launch_fast<ROCKS, MULTIROCK, false, false>(g, t, f, a, slice_lo, slice_hi, n_sms, smem, st);
+    if (cap && nn)       launch_fast<ROCKS, MULTIROCK, true, true>(g, t, f, a, halo, slice_lo, slice_hi, n_sms, smem, st);
+    else if (cap)        launch_fast<ROCKS, MULTIROCK, true, false>(g, t, f, a, halo, slice_lo, slice_hi, n_sms, smem, st);
+    else if (nn)         launch_fast<ROCKS, MULTIROCK, false, true>(g, t, f, a, halo, slice_lo, slice_hi, n_sms, smem, st);
+    else                 launch_fast<ROCKS, MULTIROCK, false, false>(g, t, f, a, halo, slice_lo, slice_hi, n_sms, smem, st);
 }
 
 void eu_launch_fast_step(const EuGridDev& g, const EuTablesDev& t, const EuFastDev& f, const EuStepArgs& a,
-                         int slice_lo, int slice_hi, int n_sms, cudaStream_t st)
+                         const EuHaloDev& halo, int slice_lo, int slice_hi, int n_sms, cudaStream_t st)
 {
     if (slice_hi <= slice_lo) return;
     const size_t smem = eu_fast_smem_bytes(t);
-    if (t.n_rocks > 1)       launch_fast2<true, true>(g, t, f, a, slice_lo, slice_hi, n_sms, smem, st);
-    else if (t.n_rocks == 1) launch_fast2<true, false>(g, t, f, a, slice_lo, slice_hi, n_sms, smem, st);
-    else                     launch_fast2<false, false>(g, t, f, a, slice_lo, slice_hi, n_sms, smem, st);
+    if (t.n_rocks > 1)       launch_fast2<true, true>(g, t, f, a, halo, slice_lo, slice_hi, n_sms, smem, st);
+    else if (t.n_rocks == 1) launch_fast2<true, false>(g, t, f, a, halo, slice_lo, slice_hi, n_sms, smem, st);
+    else                     launch_fast2<false, false>(g, t, f, a, halo, slice_lo, slice_hi, n_sms, smem, st);
 }

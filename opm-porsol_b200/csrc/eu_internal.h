@@ -114,6 +114,29 @@ struct EuStepArgs {
     double gravity[3];
 };
 
+// Halo exchange fused into the FAST substep kernel (one process per GPU, peers mapped with CUDA IPC).
+// The own slices next to a slab boundary form up to two ranges at the two ends of the own slice range; they
+// are processed FIRST, their new saturations are also stored into the neighbour's ghost slots (NVLink P2P),
+// and the last warp to finish a neighbour's share publishes the epoch in that neighbour's flag word.
+// Before touching ghosts the boundary warps wait for the neighbours' flags of the previous epoch.
+struct EuHaloDev {
+    int enabled;
+    int a_hi;                  // boundary range A = [slice_lo, a_hi)
+    int b_lo;                  // boundary range B = [b_lo, slice_hi)
+    const int* dst[2];         // per cell of the range (from its first slice): ghost slot in the peer, or -1
+    double* peer_S[2];         // the peer's S_out buffer
+    double* peer_pc[2];        // the peer's pc_out buffer (FAST + capillary) or NULL
+    unsigned* counter[2];      // finished-slice counter (shared when both ranges feed the same peer)
+    unsigned total[2];         // slices that make the counter complete
+    unsigned* peer_flag[2];    // flag word in the peer, written with `epoch`
+    const unsigned* my_flags;  // [world]: flag words the peers write
+    int n_wait;
+    int wait_rank[2];
+    unsigned epoch;
+    long long timeout_cycles;
+    int* err_flag;
+};
+
 // ---- launchers implemented in eu_setup.cu (all -fmad=false) --------------------------------
 struct EuSetupOut;   // opaque to eu_fast.cu
 void eu_launch_translate_nbr(int* hf_nbr, long long H, const int* range_first, const int* range_count,
@@ -150,7 +173,8 @@ void eu_launch_halo_wait(const unsigned* my_flags, const int* wait_ranks, int n_
 void eu_launch_fast_pc(const EuGridDev& g, const EuTablesDev& t, const EuFastDev& f, const double* S, double* pc,
                        int lo, int hi, cudaStream_t st);
 void eu_launch_fast_step(const EuGridDev& g, const EuTablesDev& t, const EuFastDev& f, const EuStepArgs& a,
-                         int slice_lo, int slice_hi, int n_sms, cudaStream_t st);
+                         const EuHaloDev& halo, int slice_lo, int slice_hi, int n_sms, cudaStream_t st);
+void eu_launch_ghost_adjacent(const EuGridDev& g, int* out4, cudaStream_t st);
 size_t eu_fast_smem_bytes(const EuTablesDev& t);
 
 #endif

@@ -621,6 +621,22 @@ __global__ void k_halo_wait(const unsigned* my_flags, const int* __restrict__ wa
     __threadfence_system();
 }
 
+// own cells that read a ghost: out[0] = max index of an own cell with a neighbour below the own range,
+// out[1] = min index of an own cell with a neighbour above it (boundary ranges of the fused halo exchange)
+__global__ void k_ghost_adjacent(EuGridDev g, int* __restrict__ out)
+{
+    int c = g.own_lo + blockIdx.x*blockDim.x + threadIdx.x;
+    if (c >= g.own_hi) return;
+    bool down = false, up = false;
+    for (int h = g.hf_offset[c]; h < g.hf_offset[c + 1]; ++h) {
+        const int n = hf_other_cell(g, c, h);
+        if (n >= 0 && n < g.own_lo) down = true;
+        if (n >= g.own_hi) up = true;
+    }
+    if (down) atomicMax(out + 0, c);
+    if (up) atomicMin(out + 1, c);
+}
+
 } // namespace
 
 // ---------------------------------------------------------------------------------------
@@ -720,4 +736,10 @@ void eu_launch_halo_wait(const unsigned* my_flags, const int* wait_ranks, int n_
 {
     if (n_wait <= 0) return;
     k_halo_wait<<<1, 32, 0, st>>>(my_flags, wait_ranks, n_wait, epoch, timeout_cycles, err_flag);
+}
+
+void eu_launch_ghost_adjacent(const EuGridDev& g, int* out4, cudaStream_t st)
+{
+    const int n = g.own_hi - g.own_lo;
+    if (n > 0) k_ghost_adjacent<<<div_up(n, kThreads), kThreads, 0, st>>>(g, out4);
 }
