@@ -307,6 +307,14 @@ def main():
         kernel_ms = dev_ms/total_substeps
         achieved = bytes_per_launch/(kernel_ms*1e-3)/1e9
         peak, peak_src = measured_peak()
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        key = "viscous+gravity+capillary" if a.capillary else "viscous+gravity"
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                tj = json.load(f)
+            if key in tj:       # dram__bytes_read + dram__bytes_write of k_fast_step per cell, from the committed ncu capture
+                traffic = tj[key]["dram_bytes_per_cell_substep"]*N/world
         line = {
             "metric": "EulerUpstream cell-substeps/s", "value": value, "unit": "cell-substeps/s",
             "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3*wall/a.steps,
@@ -316,7 +324,7 @@ def main():
                        "l2": "inputs (>= 8 GB per substep at full size) exceed the 126 MB L2; no flush needed",
                        "setup_s": round(t_setup, 1), "sat_range_after": [s_min, s_max]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved/peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "k_fast_step" if a.mode != "strict" else "k_strict_step",
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "k_fast_step" if a.mode != "strict" else "k_strict_step",
                          "bytes_per_cell_substep": bytes_per_substep_total/N, "kernel_ms": kernel_ms},
             "clocks": clocks, "gpu_launches": launches,
         }
