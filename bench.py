@@ -322,7 +322,8 @@ def main():
             "config": {"workload": workload_name(a), "cells": N, "substeps_per_step": a.substeps,
                        "parallelism": f"z-slabs x{world}", "arithmetic_mode": a.mode,
                        "l2": "inputs (>= 8 GB per substep at full size) exceed the 126 MB L2; no flush needed",
-                       "setup_s": round(t_setup, 1), "sat_range_after": [s_min, s_max]},
+                       "setup_s": round(t_setup, 1), "sat_range_after": [s_min, s_max],
+                       "regular_slot_fraction": round(dev.regular_fraction(), 4)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved/peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "k_fast_step" if a.mode != "strict" else "k_strict_step",
                          "bytes_per_cell_substep": bytes_per_substep_total/N, "kernel_ms": kernel_ms},

@@ -170,6 +170,8 @@ int eu_grid_end(eu_handle h);               /* builds the device structures */
 /* number of local cells / half-faces held by this rank, in upload order (own + ghost) */
 int eu_local_cells(eu_handle h);
 long long eu_local_halffaces(eu_handle h);
+/* fraction of (slice, slot) pairs whose adjacency is described by an 8-byte descriptor instead of 32 records */
+double eu_regular_fraction(eu_handle h);
 
 /* ---- EulerUpstream::transportSolve (EulerUpstream_impl.hpp:151-218) -------------------
  * saturation:  local cells (in/out; ghost entries are inputs only)

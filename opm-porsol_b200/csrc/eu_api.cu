@@ -84,7 +84,8 @@ struct eu_solver {
     EuTablesDev tab;
     // ---- derived
     DevBuf<int> d_owner_hf, d_fid_of_hf, d_slice_base, d_flags;
-    DevBuf<int2> d_strict_list, d_rec;
+    DevBuf<int2> d_strict_list, d_rec, d_desc;
+    double regular_fraction = 0.0;
     DevBuf<double> d_porevol, d_inv_porevol, d_pcscale, d_q, d_G, d_T, d_nn;
     DevBuf<unsigned char> d_rock8;
     long long F = 0;
@@ -150,7 +151,7 @@ struct eu_solver {
     EuFastDev fast() const
     {
         EuFastDev f;
-        f.n_slices = n_slices; f.slice_base = d_slice_base.p; f.rec = d_rec.p;
+        f.n_slices = n_slices; f.n_local = n_local; f.slice_base = d_slice_base.p; f.rec = d_rec.p; f.desc = d_desc.p;
         f.q = d_q.p; f.G = d_G.p; f.T = d_T.p; f.nn = use_nn ? d_nn.p : nullptr;
         f.inv_porevol = d_inv_porevol.p; f.pcscale = d_pcscale.p; f.rock8 = d_rock8.p; f.F = F;
         return f;
@@ -250,6 +251,12 @@ int ensure_contracted(eu_handle h, const double gravity[3])
     EU_CUDA(h, cudaStreamSynchronize(h->st));
     EU_CUDA(h, cudaGetLastError());
     h->use_nn = maxdev > 1e-13;     // non-unit normals: keep the n.n factor of the viscous term
+    if (h->use_nn && h->d_nn.n == 0) {
+        EU_CUDA(h, h->d_nn.alloc(size_t(std::max<long long>(h->F, 1))));
+        eu_launch_contract(h->grid(), h->tab, h->d_owner_hf.p, h->d_fid_of_hf.p, gravity, mg, h->d_G.p, h->d_T.p, h->d_nn.p,
+                           h->d_scalars.p + 8, h->st);
+        EU_CUDA(h, cudaStreamSynchronize(h->st));
+    }
     h->contracted = true;
     h->contracted_mg = mg;
     std::memcpy(h->contracted_gravity, gravity, 3*sizeof(double));
@@ -513,6 +520,7 @@ int eu_grid_begin(eu_handle h, int n_cells_global, int n_local_cells, long long 
     h->h_hf_offset.reserve(size_t(n_local_cells) + 1);
     h->b_hf.clear(); h->b_kind.clear(); h->b_pcell.clear(); h->b_pface.clear(); h->b_sat.clear();
     h->any_rock_ids = false;
+    h->d_nn.release();
     const size_t n = size_t(n_local_cells), H = size_t(n_local_halffaces);
     EU_CUDA(h, h->d_hf_nbr.alloc(H));
     EU_CUDA(h, h->d_hf_area.alloc(H));
@@ -764,35 +772,41 @@ int eu_grid_end(eu_handle h)
         EU_CUDA(h, cudaMemsetAsync(h->d_fid_of_hf.p, 0xff, H*sizeof(int), h->st));
     } else {
         h->n_slices = (h->n_local + EU_SLICE - 1)/EU_SLICE;
-        DevBuf<int> d_width, d_nown, d_fid_base;
+        DevBuf<int> d_width, d_nown;
         EU_CUDA(h, d_width.alloc(size_t(h->n_slices)));
         EU_CUDA(h, d_nown.alloc(size_t(h->n_slices)));
         eu_launch_slice_count(g, h->d_owner_hf.p, d_width.p, d_nown.p, h->st);
-        std::vector<int> width(size_t(h->n_slices)), nown(size_t(h->n_slices));
+        std::vector<int> width(size_t(h->n_slices));
         EU_CUDA(h, cudaMemcpyAsync(width.data(), d_width.p, width.size()*sizeof(int), cudaMemcpyDeviceToHost, h->st));
-        EU_CUDA(h, cudaMemcpyAsync(nown.data(), d_nown.p, nown.size()*sizeof(int), cudaMemcpyDeviceToHost, h->st));
         EU_CUDA(h, cudaStreamSynchronize(h->st));
-        std::vector<int> base(size_t(h->n_slices) + 1), fbase(size_t(h->n_slices));
-        long long rec_total = 0, f_total = 0;
+        std::vector<int> base(size_t(h->n_slices) + 1);
+        long long rec_total = 0;
+        int planes = 1;
         for (int s = 0; s < h->n_slices; ++s) {
             base[size_t(s)] = int(rec_total);
-            fbase[size_t(s)] = int(f_total);
             rec_total += (long long)width[size_t(s)]*EU_SLICE;
-            f_total += nown[size_t(s)];
+            planes = std::max(planes, width[size_t(s)]);
             if (rec_total > INT_MAX) return fail(h, EU_ERR_UNSUPPORTED, "too many half-face records for one GPU (32-bit)");
         }
         base[size_t(h->n_slices)] = int(rec_total);
-        h->F = f_total;
+        // unique-face arrays: one plane per local face slot, indexed plane*n_local + owner cell
+        h->F = (long long)planes*h->n_local;
+        if (h->F > INT_MAX) return fail(h, EU_ERR_UNSUPPORTED, "face planes exceed 32-bit indexing on one GPU");
         if ((rc = upload_vec(h, h->d_slice_base, base))) return rc;
-        if ((rc = upload_vec(h, d_fid_base, fbase))) return rc;
         EU_CUDA(h, h->d_rec.alloc(size_t(rec_total)));
-        eu_launch_assign_fid(g, h->d_owner_hf.p, d_fid_base.p, h->d_fid_of_hf.p, h->st);
-        eu_launch_build_records(g, h->d_owner_hf.p, h->d_fid_of_hf.p, h->d_slice_base.p, h->d_rec.p, h->st);
+        EU_CUDA(h, h->d_desc.alloc(size_t(rec_total/EU_SLICE) + 1));
+        EU_CUDA(h, cudaMemsetAsync(h->d_flags.p, 0, 4*sizeof(int), h->st));
+        eu_launch_assign_fid(g, h->d_owner_hf.p, h->d_fid_of_hf.p, h->st);
+        eu_launch_build_records(g, h->d_owner_hf.p, h->d_fid_of_hf.p, h->d_slice_base.p, h->d_rec.p, h->d_desc.p,
+                                h->d_flags.p + 1, h->st);
+        int nreg[4] = { 0, 0, 0, 0 };
+        EU_CUDA(h, cudaMemcpyAsync(nreg, h->d_flags.p, sizeof(nreg), cudaMemcpyDeviceToHost, h->st));
+        EU_CUDA(h, cudaStreamSynchronize(h->st));
+        h->regular_fraction = rec_total > 0 ? double(nreg[1])/double(rec_total/EU_SLICE) : 0.0;
         const size_t F = size_t(std::max<long long>(h->F, 1));
         EU_CUDA(h, h->d_q.alloc(F));
         EU_CUDA(h, h->d_G.alloc(F));
         EU_CUDA(h, h->d_T.alloc(F));
-        EU_CUDA(h, h->d_nn.alloc(F));
         EU_CUDA(h, h->d_pcscale.alloc(n));
         EU_CUDA(h, h->d_rock8.alloc(n));
         EU_CUDA(h, h->d_inv_porevol.alloc(n));
@@ -820,6 +834,7 @@ int eu_grid_end(eu_handle h)
 }
 
 int eu_local_cells(eu_handle h) { return h ? h->n_local : 0; }
+double eu_regular_fraction(eu_handle h) { return h ? h->regular_fraction : 0.0; }
 long long eu_local_halffaces(eu_handle h) { return h ? h->H : 0; }
 
 int eu_upload_saturation(eu_handle h, const double* saturation)

@@ -123,8 +123,8 @@ __device__ __forceinline__ double face_contribution(bool own, bool interior, dou
                                                     double cap_coef /* lam_w lam_o / lam_t at the average saturation */,
                                                     double Tdpc /* T*(pc_hi - pc_lo) */)
 {
+    // straight-line code (selects only) so that the faces of a batch can be interleaved by the scheduler
     const bool triv_w = G >= 0.0;
-    // mobilities of the trivial (t) and the other (n) phase on both sides
     const double t0 = triv_w ? lw0 : lo0, t1 = triv_w ? lw1 : lo1;
     const double n0 = triv_w ? lo0 : lw0, n1 = triv_w ? lo1 : lw1;
     const bool u_self = (q >= 0.0) == own;                 // upstream cell of the trivial phase is self
@@ -135,21 +135,38 @@ __device__ __forceinline__ double face_contribution(bool own, bool interior, dou
     const double lw = triv_w ? lam_t : lam_n;
     const double lo = triv_w ? lam_n : lam_t;
     double num = method_viscous ? qq : 0.0;
-    if (method_gravity && interior) num = fma(lo, G, num);
+    num = (method_gravity && interior) ? fma(lo, G, num) : num;
     double dS = div_pos(lw*num, lam_t + lam_n);
-    if (CAP && interior) dS = fma(cap_coef, Tdpc, dS);
+    if (CAP) dS = interior ? fma(cap_coef, Tdpc, dS) : dS;
     return own ? -dS : dS;
 }
 
 template <bool ROCKS, bool MULTIROCK, bool CAP, bool NN, int W, int B>
 __device__ __forceinline__ double gather_cell(const TabLayout& L, const EuGridDev& g, const EuTablesDev& t,
                                               const EuFastDev& f, const EuStepArgs& a, const int2* __restrict__ recp,
-                                              int width, int c, double S0, int rock0, double pc0)
+                                              const int2* __restrict__ dscp, int width, int c, double S0, int rock0, double pc0)
 {
-    // phase A: all records of the cell
-    int2 r[W];
+    // phase A: the cell's records.  Regular slots come from the 8-byte slice descriptor (neighbour = c + d,
+    // face id affine in c): no per-cell record is read; irregular slots (boundaries, faults) load theirs.
+    // All descriptors are fetched before any of them is looked at (they are warp-uniform broadcast loads).
+    int2 dsc[W];
 #pragma unroll
-    for (int j = 0; j < W; ++j) r[j] = (j < width) ? __ldg(recp + j*EU_SLICE) : make_int2(EU_REC_PAD, -1);
+    for (int j = 0; j < W; ++j) dsc[j] = __ldg(dscp + (j < width ? j : 0));
+    int2 r[W];
+    bool any_explicit = false;
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+        const int nb = c + dsc[j].x;
+        const bool regular = (j < width) && dsc[j].y >= 0;
+        r[j].x = regular ? nb : EU_REC_PAD;
+        r[j].y = dsc[j].y*f.n_local + (dsc[j].x > 0 ? c : nb);
+        any_explicit |= (j < width) && dsc[j].y == -1;
+    }
+    if (any_explicit) {                       // warp-uniform: only slices at boundaries / faults
+#pragma unroll
+        for (int j = 0; j < W; ++j)
+            if (j < width && dsc[j].y == -1) r[j] = __ldg(recp + j*EU_SLICE);
+    }
     double lw0, lo0;
     Mob<ROCKS, MULTIROCK>::both(L, t, rock0, S0, lw0, lo0);
     double acc = 0.0;
@@ -178,18 +195,19 @@ __device__ __forceinline__ double gather_cell(const TabLayout& L, const EuGridDe
                 }
             }
         }
-        // phase C: arithmetic
+        // phase C: arithmetic, branch-free per face (an absent face contributes an exact zero)
 #pragma unroll
         for (int k = 0; k < B; ++k) {
             const int j = j0 + k;
-            if (j >= W || r[j].x == EU_REC_PAD) continue;
+            if (j >= W) continue;                              // compile-time
+            const bool valid = r[j].x != EU_REC_PAD;
             const bool interior = r[j].x >= 0;
             const bool own = !interior || c < r[j].x;
             const int rk1 = MULTIROCK ? rk[k] : 0;
             double lw1, lo1;
             Mob<ROCKS, MULTIROCK>::both(L, t, rk1, S1[k], lw1, lo1);
             double cap_coef = 0.0, Tdpc = 0.0;
-            if (CAP && interior) {
+            if (CAP) {
                 const double Sa = 0.5*(S0 + S1[k]);
                 double lwa, loa;
                 Mob<ROCKS, MULTIROCK>::both(L, t, rock0, Sa, lwa, loa);
@@ -202,8 +220,9 @@ __device__ __forceinline__ double gather_cell(const TabLayout& L, const EuGridDe
                 cap_coef = div_pos(lwa*loa, lwa + loa);
                 Tdpc = T[k]*(own ? (pc1[k] - pc0) : (pc0 - pc1[k]));
             }
-            acc += face_contribution<CAP>(own, interior, q[k], NN ? q[k]*nn[k] : q[k], G[k], lw0, lo0, lw1, lo1,
-                                          a.method_viscous, a.method_gravity, cap_coef, Tdpc);
+            const double contrib = face_contribution<CAP>(own, interior, q[k], NN ? q[k]*nn[k] : q[k], G[k], lw0, lo0, lw1, lo1,
+                                                          a.method_viscous, a.method_gravity, cap_coef, Tdpc);
+            acc += valid ? contrib : 0.0;
         }
     }
     return acc;
@@ -302,9 +321,10 @@ __global__ void __launch_bounds__(kBlock, MINB) k_fast_step(EuGridDev g, EuTable
         const double pc0 = CAP ? a.pc_in[c] : 0.0;
         const double inv_pv = f.inv_porevol[c];
         const int2* __restrict__ recp = f.rec + base + lane;
+        const int2* __restrict__ dscp = f.desc + (base >> 5);
         double acc;
-        if (width <= 6)      acc = gather_cell<ROCKS, MULTIROCK, CAP, NN, 6, B6>(L, g, t, f, a, recp, width, c, S0, rock0, pc0);
-        else if (width <= 8) acc = gather_cell<ROCKS, MULTIROCK, CAP, NN, 8, B8>(L, g, t, f, a, recp, width, c, S0, rock0, pc0);
+        if (width <= 6)      acc = gather_cell<ROCKS, MULTIROCK, CAP, NN, 6, B6>(L, g, t, f, a, recp, dscp, width, c, S0, rock0, pc0);
+        else if (width <= 8) acc = gather_cell<ROCKS, MULTIROCK, CAP, NN, 8, B8>(L, g, t, f, a, recp, dscp, width, c, S0, rock0, pc0);
         else                 acc = gather_cell_loop<ROCKS, MULTIROCK, CAP, NN>(L, g, t, f, a, recp, width, c, S0, rock0, pc0);
 
         double rate = 0.0;

@@ -85,8 +85,12 @@ struct EuStrictDev {
 
 struct EuFastDev {
     int n_slices;             // slices over all local cells
-    const int* slice_base;    // n_slices+1, record offsets
-    const int2* rec;
+    int n_local;              // face id = plane*n_local + owner cell, plane = the owner's local face slot
+    const int* slice_base;    // n_slices+1, record offsets (multiples of 32)
+    const int2* rec;          // explicit records, read only for the slots a descriptor marks irregular
+    const int2* desc;         // per (slice, slot) at slice_base/32 + slot: {d, k}.  k >= 0: every lane's neighbour
+                              // is cell + d and its face lives in plane k (regular slot, no record needed);
+                              // k == -1: irregular slot, use rec; k == -2: no face in this slot
     const double* q;          // compacted flux of the current transportSolve
     const double* G;
     const double* T;
@@ -145,9 +149,9 @@ void eu_launch_owner(const EuGridDev& g, int* owner_hf, int* err_flag, cudaStrea
 void eu_launch_strict_list(const EuGridDev& g, const int* owner_hf, int2* list, cudaStream_t st);
 void eu_launch_porevol(const EuGridDev& g, double* porevol, cudaStream_t st);
 void eu_launch_slice_count(const EuGridDev& g, const int* owner_hf, int* slice_width, int* slice_nown, cudaStream_t st);
-void eu_launch_assign_fid(const EuGridDev& g, const int* owner_hf, const int* slice_fid_base, int* fid_of_hf, cudaStream_t st);
+void eu_launch_assign_fid(const EuGridDev& g, const int* owner_hf, int* fid_of_hf, cudaStream_t st);
 void eu_launch_build_records(const EuGridDev& g, const int* owner_hf, const int* fid_of_hf, const int* slice_base,
-                             int2* rec, cudaStream_t st);
+                             int2* rec, int2* desc, int* n_regular_slots, cudaStream_t st);
 void eu_launch_contract(const EuGridDev& g, const EuTablesDev& t, const int* owner_hf, const int* fid_of_hf,
                         const double gravity[3], int method_gravity, double* G, double* T, double* nn,
                         double* nn_maxdev, cudaStream_t st);

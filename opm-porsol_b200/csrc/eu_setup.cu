@@ -148,32 +148,19 @@ __global__ void k_slice_count(EuGridDev g, const int* __restrict__ owner_hf, int
     if (lane == 0) { slice_width[warp] = cnt; slice_nown[warp] = nown; }
 }
 
-// unique face ids in (slice, slot, lane) order, so that the owner faces of one slot of a
-// slice are contiguous in the face arrays
-__global__ void k_assign_fid(EuGridDev g, const int* __restrict__ owner_hf, const int* __restrict__ slice_fid_base,
-                             int* __restrict__ fid_of_hf)
+// face id of an own half-face = slot*n_local + cell ("plane" = local face slot of the owner): coalesced per
+// plane, and for a regular neighbour pattern the id of the neighbour's twin face is affine in the cell index
+__global__ void k_assign_fid(EuGridDev g, const int* __restrict__ owner_hf, int* __restrict__ fid_of_hf)
 {
-    const int warp = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    const int n_slices = (g.n_local + EU_SLICE - 1)/EU_SLICE;
-    if (warp >= n_slices) return;
-    const int c = warp*EU_SLICE + lane;
-    int b = 0, cnt = 0;
-    if (c < g.n_local) { b = g.hf_offset[c]; cnt = g.hf_offset[c + 1] - b; }
-    int width = cnt;
-    for (int o = 16; o > 0; o >>= 1) width = max(width, __shfl_xor_sync(0xffffffffu, width, o));
-    int running = slice_fid_base[warp];
-    for (int j = 0; j < width; ++j) {
-        const bool has = j < cnt;
-        const bool is_owner = has && owner_hf[b + j] == b + j;
-        const unsigned mask = __ballot_sync(0xffffffffu, is_owner);
-        if (has) fid_of_hf[b + j] = is_owner ? running + __popc(mask & ((1u << lane) - 1u)) : -1;
-        running += __popc(mask);
-    }
+    int c = blockIdx.x*blockDim.x + threadIdx.x;
+    if (c >= g.n_local) return;
+    const int b = g.hf_offset[c], e = g.hf_offset[c + 1];
+    for (int h = b; h < e; ++h) fid_of_hf[h] = (owner_hf[h] == h) ? (h - b)*g.n_local + c : -1;
 }
 
 __global__ void k_build_records(EuGridDev g, const int* __restrict__ owner_hf, const int* __restrict__ fid_of_hf,
-                                const int* __restrict__ slice_base, int2* __restrict__ rec)
+                                const int* __restrict__ slice_base, int2* __restrict__ rec, int2* __restrict__ desc,
+                                int* __restrict__ n_regular_slots)
 {
     const int warp = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -201,6 +188,19 @@ __global__ void k_build_records(EuGridDev g, const int* __restrict__ owner_hf, c
             }
         }
         rec[(long long)base + (long long)j*EU_SLICE + lane] = r;
+        // regular slot: every lane has an interior (or periodic) neighbour at the same offset d whose face
+        // lives in the same plane k, so that nbr = c + d and fid = k*n_local + (d > 0 ? c : c + d)
+        const int d = r.x - c;
+        const int k = (r.x >= 0 && r.y >= 0) ? r.y/g.n_local : -1;
+        const int d0 = __shfl_sync(0xffffffffu, d, 0), k0 = __shfl_sync(0xffffffffu, k, 0);
+        const bool lane_ok = c < g.n_local && r.x >= 0 && k >= 0 && d == d0 && k == k0 && d != 0 &&
+                             r.y == k*g.n_local + (d > 0 ? c : r.x);
+        const bool regular = __all_sync(0xffffffffu, lane_ok);
+        const bool any = __any_sync(0xffffffffu, r.x != EU_REC_PAD);
+        if (lane == 0) {
+            desc[base/EU_SLICE + j] = regular ? make_int2(d0, k0) : make_int2(0, any ? -1 : -2);
+            if (regular) atomicAdd(n_regular_slots, 1);
+        }
     }
 }
 
@@ -251,7 +251,7 @@ __global__ void k_contract(EuGridDev g, EuTablesDev t, const int* __restrict__ o
         }
         T[fid] = Tv;
         const double nnv = sm_inner3(nrm, nrm);
-        nn[fid] = nnv;
+        if (nn) nn[fid] = nnv;
         maxdev = fmax(maxdev, fabs(nnv - 1.0));
     }
     if (maxdev > 0.0) atomicMax(nn_maxdev_bits, (unsigned long long)__double_as_longlong(maxdev));
@@ -663,16 +663,16 @@ void eu_launch_slice_count(const EuGridDev& g, const int* owner_hf, int* slice_w
     const int n_slices = (g.n_local + EU_SLICE - 1)/EU_SLICE;
     k_slice_count<<<div_up((long long)n_slices*32, kThreads), kThreads, 0, st>>>(g, owner_hf, slice_width, slice_nown);
 }
-void eu_launch_assign_fid(const EuGridDev& g, const int* owner_hf, const int* slice_fid_base, int* fid_of_hf, cudaStream_t st)
+void eu_launch_assign_fid(const EuGridDev& g, const int* owner_hf, int* fid_of_hf, cudaStream_t st)
 {
-    const int n_slices = (g.n_local + EU_SLICE - 1)/EU_SLICE;
-    k_assign_fid<<<div_up((long long)n_slices*32, kThreads), kThreads, 0, st>>>(g, owner_hf, slice_fid_base, fid_of_hf);
+    k_assign_fid<<<div_up(g.n_local, kThreads), kThreads, 0, st>>>(g, owner_hf, fid_of_hf);
 }
 void eu_launch_build_records(const EuGridDev& g, const int* owner_hf, const int* fid_of_hf, const int* slice_base,
-                             int2* rec, cudaStream_t st)
+                             int2* rec, int2* desc, int* n_regular_slots, cudaStream_t st)
 {
     const int n_slices = (g.n_local + EU_SLICE - 1)/EU_SLICE;
-    k_build_records<<<div_up((long long)n_slices*32, kThreads), kThreads, 0, st>>>(g, owner_hf, fid_of_hf, slice_base, rec);
+    k_build_records<<<div_up((long long)n_slices*32, kThreads), kThreads, 0, st>>>(g, owner_hf, fid_of_hf, slice_base, rec, desc,
+                                                                                  n_regular_slots);
 }
 void eu_launch_contract(const EuGridDev& g, const EuTablesDev& t, const int* owner_hf, const int* fid_of_hf,
                         const double gravity[3], int method_gravity, double* G, double* T, double* nn,

@@ -108,6 +108,8 @@ def load_library():
     L.eu_local_cells.argtypes = [C.c_void_p]
     L.eu_local_halffaces.argtypes = [C.c_void_p]
     L.eu_local_halffaces.restype = C.c_longlong
+    L.eu_regular_fraction.argtypes = [C.c_void_p]
+    L.eu_regular_fraction.restype = C.c_double
     L.eu_transport_solve.argtypes = [C.c_void_p, _dp, C.c_double, _dp, _dp, C.c_int, _ip, _dp, C.POINTER(_Report)]
     L.eu_upload_state.argtypes = [C.c_void_p, _dp, _dp]
     L.eu_upload_saturation.argtypes = [C.c_void_p, _dp]
@@ -360,6 +362,9 @@ class EulerUpstream:
         if rc != EU_OK and raise_on_error:
             raise EulerB200Error(rc, self.L.eu_last_error(self.h).decode())
         return self.last_report
+
+    def regular_fraction(self):
+        return float(self.L.eu_regular_fraction(self.h))
 
     def cfl_times(self, gravity):
         g = np.ascontiguousarray(gravity, dtype=np.float64)
