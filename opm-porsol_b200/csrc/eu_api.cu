@@ -14,7 +14,10 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <limits>
+#include <map>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -86,7 +89,15 @@ struct eu_solver {
     DevBuf<int> d_owner_hf, d_fid_of_hf, d_slice_base, d_flags;
     DevBuf<int2> d_strict_list, d_rec, d_desc;
     double regular_fraction = 0.0;
-    DevBuf<double> d_porevol, d_inv_porevol, d_pcscale, d_q, d_G, d_T, d_nn;
+    // work items of the FAST kernel (slice classes + marches), built for the slice range [items_lo, items_hi)
+    std::vector<int> h_slice_base;
+    DevBuf<int2> d_items;
+    DevBuf<EuSliceClass> d_classes;
+    int n_items = 0, n_classes = 0, items_lo = -1, items_hi = -1;
+    double class_fraction = 0.0;       // share of the own slices that belong to a slice class
+    DevBuf<double> d_porevol, d_inv_porevol, d_pcscale, d_T, d_nn;
+    DevBuf<double2> d_lam[2];          // per cell {lambda_w, lambda_o} of the state in d_S[k] (FAST)
+    DevBuf<double2> d_qg;              // per unique face {flux of the current transportSolve, G}
     DevBuf<unsigned char> d_rock8;
     long long F = 0;
     int n_slices = 0;
@@ -151,8 +162,9 @@ struct eu_solver {
     EuFastDev fast() const
     {
         EuFastDev f;
-        f.n_slices = n_slices; f.n_local = n_local; f.slice_base = d_slice_base.p; f.rec = d_rec.p; f.desc = d_desc.p;
-        f.q = d_q.p; f.G = d_G.p; f.T = d_T.p; f.nn = use_nn ? d_nn.p : nullptr;
+        f.n_slices = n_slices; f.n_local = n_local; f.items = d_items.p; f.n_items = n_items;
+        f.classes = d_classes.p; f.n_classes = n_classes; f.slice_base = d_slice_base.p; f.rec = d_rec.p; f.desc = d_desc.p;
+        f.qg = d_qg.p; f.T = d_T.p; f.nn = use_nn ? d_nn.p : nullptr;
         f.inv_porevol = d_inv_porevol.p; f.pcscale = d_pcscale.p; f.rock8 = d_rock8.p; f.F = F;
         return f;
     }
@@ -244,7 +256,7 @@ int ensure_contracted(eu_handle h, const double gravity[3])
     const int mg = h->par.method_gravity ? 1 : 0;
     if (h->contracted && h->contracted_mg == mg && std::memcmp(h->contracted_gravity, gravity, 3*sizeof(double)) == 0)
         return EU_OK;
-    eu_launch_contract(h->grid(), h->tab, h->d_owner_hf.p, h->d_fid_of_hf.p, gravity, mg, h->d_G.p, h->d_T.p, h->d_nn.p,
+    eu_launch_contract(h->grid(), h->tab, h->d_owner_hf.p, h->d_fid_of_hf.p, gravity, mg, reinterpret_cast<double*>(h->d_qg.p) + 1, h->d_T.p, h->d_nn.p,
                        h->d_scalars.p + 8, h->st);
     double maxdev = 0.0;
     EU_CUDA(h, cudaMemcpyAsync(&maxdev, h->d_scalars.p + 8, sizeof(double), cudaMemcpyDeviceToHost, h->st));
@@ -252,8 +264,9 @@ int ensure_contracted(eu_handle h, const double gravity[3])
     EU_CUDA(h, cudaGetLastError());
     h->use_nn = maxdev > 1e-13;     // non-unit normals: keep the n.n factor of the viscous term
     if (h->use_nn && h->d_nn.n == 0) {
-        EU_CUDA(h, h->d_nn.alloc(size_t(std::max<long long>(h->F, 1))));
-        eu_launch_contract(h->grid(), h->tab, h->d_owner_hf.p, h->d_fid_of_hf.p, gravity, mg, h->d_G.p, h->d_T.p, h->d_nn.p,
+        EU_CUDA(h, h->d_nn.alloc(size_t(std::max<long long>(h->F, 1)) + 1));
+        EU_CUDA(h, cudaMemsetAsync(h->d_nn.p, 0, h->d_nn.n*sizeof(double), h->st));
+        eu_launch_contract(h->grid(), h->tab, h->d_owner_hf.p, h->d_fid_of_hf.p, gravity, mg, reinterpret_cast<double*>(h->d_qg.p) + 1, h->d_T.p, h->d_nn.p,
                            h->d_scalars.p + 8, h->st);
         EU_CUDA(h, cudaStreamSynchronize(h->st));
     }
@@ -295,6 +308,7 @@ EuStepArgs step_args(eu_handle h, double dt, const double gravity[3], int n_src,
     a.n_src = n_src; a.src_cell = h->d_src_cell.p; a.src_rate = h->d_src_rate.p;
     a.S_in = h->d_S[h->cur].p; a.S_out = h->d_S[h->cur ^ 1].p;
     a.pc_in = h->d_pc[h->cur].p; a.pc_out = h->d_pc[h->cur ^ 1].p;
+    a.lam_in = h->d_lam[h->cur].p; a.lam_out = h->d_lam[h->cur ^ 1].p;
     a.residual_out = nullptr;
     a.fail_key = h->d_fail_key.p;
     a.gravity[0] = gravity[0]; a.gravity[1] = gravity[1]; a.gravity[2] = gravity[2];
@@ -304,6 +318,168 @@ EuStepArgs step_args(eu_handle h, double dt, const double gravity[3], int n_src,
 bool fused_halo(eu_handle h)
 {
     return h->cfg.world_size > 1 && h->comm_ready && h->mode == EU_MODE_FAST && h->fused_ok;
+}
+
+// ---- work items of the FAST kernel -----------------------------------------------------------------------
+// Classifies the slices of [lo, hi) (EuSliceClass in eu_internal.h), chains slices of the same class along the
+// march direction into items of at most `lmax` slices and orders the items so that the eight warps of a block
+// work on eight neighbouring grid rows.  Everything is derived from the CSR adjacency as uploaded (through the
+// per-slot descriptors of eu_setup.cu); a slice that fits no class stays a generic item.
+struct ClassKey {
+    int v[20];
+    bool operator<(const ClassKey& o) const { return std::memcmp(v, o.v, sizeof(v)) < 0; }
+};
+
+int build_items(eu_handle h, int lo, int hi)
+{
+    if (h->items_lo == lo && h->items_hi == hi) return EU_OK;
+    const std::vector<int>& base = h->h_slice_base;
+    const size_t n_desc = size_t(base.back()/EU_SLICE);
+    std::vector<int2> desc(n_desc + 1);
+    EU_CUDA(h, cudaMemcpy(desc.data(), h->d_desc.p, n_desc*sizeof(int2), cudaMemcpyDeviceToHost));
+    const int zero_face = int(std::max<long long>(h->F, 1));
+    std::map<ClassKey, int> class_of_key;
+    std::vector<EuSliceClass> classes;
+    std::vector<unsigned short> cls(size_t(std::max(hi - lo, 0)), (unsigned short)EU_ITEM_GENERIC);
+    const char* env_noclass = getenv("EU_NO_CLASSES");
+    // the marches read the neighbours' stored mobilities, which exist for own cells only: slice classes are used when
+    // no item touches a ghost cell (one rank, or the fused exchange whose boundary ranges take the generic path)
+    const bool use_classes = !(env_noclass && atoi(env_noclass) != 0) && (h->cfg.world_size <= 1 || fused_halo(h));
+    for (int s = lo; s < hi && use_classes; ++s) {
+        if (s*EU_SLICE < h->own_lo || (s + 1)*EU_SLICE > h->own_hi) continue;
+        if (base[size_t(s) + 1] - base[size_t(s)] != 6*EU_SLICE) continue;
+        const int2* d = &desc[size_t(base[size_t(s)]/EU_SLICE)];
+        // regular slots in (-d, +d) pairs
+        int mag[3] = { 0, 0, 0 }, neg[3] = { -1, -1, -1 }, pos[3] = { -1, -1, -1 }, npairs = 0;
+        bool ok = true;
+        for (int j = 0; j < 6 && ok; ++j) {
+            if (d[j].y < 0) continue;
+            const int m = std::abs(d[j].x);
+            int p = 0;
+            while (p < npairs && mag[p] != m) ++p;
+            if (p == npairs) {
+                if (npairs == 3) { ok = false; break; }
+                mag[npairs++] = m;
+            }
+            int& member = d[j].x < 0 ? neg[p] : pos[p];
+            if (member >= 0) ok = false;
+            member = j;
+        }
+        if (!ok) continue;
+        // march pair: the largest offset that is a whole number of slices; the other pairs by ascending offset
+        int order[3] = { 0, 1, 2 };
+        std::sort(order, order + npairs, [&](int a, int b) { return mag[a] < mag[b]; });
+        int march = -1;
+        for (int k = npairs - 1; k >= 0; --k) if (mag[order[k]] % EU_SLICE == 0) { march = order[k]; break; }
+        int slot_of_pos[6] = { -1, -1, -1, -1, -1, -1 };      // position -> original regular slot
+        int npos = 0;
+        for (int k = 0; k < npairs; ++k) {
+            const int p = order[k];
+            if (p == march) continue;
+            slot_of_pos[2*npos] = neg[p];
+            slot_of_pos[2*npos + 1] = pos[p];
+            ++npos;
+        }
+        if (march >= 0) { slot_of_pos[4] = neg[march]; slot_of_pos[5] = pos[march]; }
+        ClassKey key;
+        std::memset(&key, 0, sizeof(key));
+        EuSliceClass c;
+        std::memset(&c, 0, sizeof(c));
+        for (int q = 0; q < 6; ++q) {
+            const int j = slot_of_pos[q];
+            if (j >= 0) {
+                c.nb_off[q] = d[j].x;
+                c.fid_mul[q] = 1;
+                const long long off = (long long)d[j].y*h->n_local + (d[j].x > 0 ? 0 : d[j].x);
+                c.fid_off[q] = int(off);
+            } else {
+                c.nb_off[q] = 0; c.fid_mul[q] = 0; c.fid_off[q] = zero_face;
+            }
+            key.v[3*q] = c.nb_off[q]; key.v[3*q + 1] = c.fid_mul[q]; key.v[3*q + 2] = c.fid_off[q];
+        }
+        for (int j = 0; j < 6; ++j) if (d[j].y == -1) c.rec_mask |= 1 << j;
+        c.D = (march >= 0 && pos[march] >= 0) ? mag[march] : 0;
+        key.v[18] = c.rec_mask; key.v[19] = c.D;
+        auto it = class_of_key.find(key);
+        int id;
+        if (it != class_of_key.end()) {
+            id = it->second;
+        } else {
+            if (classes.size() >= EU_MAX_CLASSES) continue;
+            id = int(classes.size());
+            classes.push_back(c);
+            class_of_key[key] = id;
+        }
+        cls[size_t(s - lo)] = (unsigned short)id;
+    }
+    // chains along the march direction
+    const int n_warps = h->n_sms*32;
+    int lmax = 32;
+    {
+        const char* e = getenv("EU_MARCH_LEN");
+        if (e && atoi(e) > 0) lmax = std::min(atoi(e), 4096);
+        else while (lmax > 2 && (hi - lo)/lmax < 6*n_warps) lmax /= 2;
+    }
+    std::vector<int2> items;
+    std::vector<char> taken(cls.size(), 0);
+    long long n_class_slices = 0;
+    for (int s = lo; s < hi; ++s) {
+        if (taken[size_t(s - lo)]) continue;
+        const int id = cls[size_t(s - lo)];
+        int len = 1;
+        if (id != EU_ITEM_GENERIC) {
+            const int step = classes[size_t(id)].D/EU_SLICE;
+            if (step > 0) {
+                int nxt = s + step;
+                while (len < lmax && nxt < hi && !taken[size_t(nxt - lo)] && cls[size_t(nxt - lo)] == id) {
+                    taken[size_t(nxt - lo)] = 1;
+                    ++len;
+                    nxt += step;
+                }
+            }
+            n_class_slices += len;
+        }
+        taken[size_t(s - lo)] = 1;
+        items.push_back(make_int2(s, len | (id << 16)));
+    }
+    // row tiles: where 8*R consecutive items start at consecutive slices (R = slices per grid row, the second
+    // largest slice-aligned offset of the class), reorder them as R groups of 8 rows so that the warps of a block
+    // share their y-neighbour lines in L1
+    {
+        const char* e = getenv("EU_ROW_TILES");
+        const bool tiles = !(e && atoi(e) == 0);
+        size_t i = 0;
+        std::vector<int2> tmp;
+        while (tiles && i < items.size()) {
+            const int id = int(unsigned(items[i].y) >> 16);
+            int R = 0;
+            if (id != EU_ITEM_GENERIC) {
+                const EuSliceClass& c = classes[size_t(id)];
+                for (int q = 0; q < 4; ++q)
+                    if (c.fid_mul[q] && c.nb_off[q] > EU_SLICE && c.nb_off[q] % EU_SLICE == 0 && c.nb_off[q] != c.D)
+                        R = (R == 0) ? c.nb_off[q]/EU_SLICE : std::min(R, c.nb_off[q]/EU_SLICE);
+            }
+            const size_t group = size_t(8)*size_t(R);
+            bool uniform = R >= 2 && i + group <= items.size();
+            for (size_t k = 1; uniform && k < group; ++k)
+                uniform = items[i + k].x == items[i].x + int(k) && int(unsigned(items[i + k].y) >> 16) != EU_ITEM_GENERIC;
+            if (!uniform) { ++i; continue; }
+            tmp.assign(items.begin() + long(i), items.begin() + long(i + group));
+            for (size_t p = 0; p < group; ++p) items[i + p] = tmp[(p & 7)*size_t(R) + (p >> 3)];
+            i += group;
+        }
+    }
+    h->n_items = int(items.size());
+    h->n_classes = int(classes.size());
+    h->class_fraction = hi > lo ? double(n_class_slices)/double(hi - lo) : 0.0;
+    if (items.empty()) items.push_back(make_int2(0, 0));
+    if (classes.empty()) { EuSliceClass c; std::memset(&c, 0, sizeof(c)); classes.push_back(c); }
+    int rc;
+    if ((rc = upload_vec(h, h->d_items, items))) return rc;
+    if ((rc = upload_vec(h, h->d_classes, classes))) return rc;
+    h->items_lo = lo;
+    h->items_hi = hi;
+    return EU_OK;
 }
 
 // one substep on the resident state; returns the number of kernels launched.  In FAST mode with several
@@ -316,7 +492,10 @@ int launch_substep(eu_handle h, const EuStepArgs& a, bool exchange)
         const int slice_hi = (h->own_hi + EU_SLICE - 1)/EU_SLICE;
         EuHaloDev halo;
         std::memset(&halo, 0, sizeof(halo));
-        if (exchange && fused_halo(h)) {
+        const bool fused = exchange && fused_halo(h);
+        // the items cover the slices that are not handled as slab-boundary ranges
+        if (build_items(h, fused ? h->fused_a_hi : slice_lo, fused ? h->fused_b_lo : slice_hi) != EU_OK) return -1;
+        if (fused) {
             const int out = h->cur ^ 1;
             halo.enabled = 1;
             halo.a_hi = h->fused_a_hi;
@@ -388,7 +567,7 @@ int compute_cfl(eu_handle h, const double gravity[3], bool want_v, bool want_g, 
     // The velocity pass also compacts the half-face fluxes for the FAST kernel, so it always runs.
     EU_CUDA(h, cudaMemsetAsync(h->d_flags.p, 0, 4*sizeof(int), h->st));
     eu_launch_cfl_velocity_compact(g, h->fluid.cfl_factor[0], h->d_hf_flux.p, h->d_fid_of_hf.p,
-                                   h->mode == EU_MODE_FAST ? h->d_q.p : nullptr, h->d_block_min.p, h->d_flags.p,
+                                   h->mode == EU_MODE_FAST ? reinterpret_cast<double*>(h->d_qg.p) : nullptr, h->d_block_min.p, h->d_flags.p,
                                    h->d_scalars.p + 0, h->st);
     *launches += 2;
     const bool grav_cached = h->cfl_grav_valid && std::memcmp(h->cfl_grav_gravity, gravity, 3*sizeof(double)) == 0;
@@ -474,10 +653,10 @@ int eu_create(const eu_config* cfg, eu_handle* out)
     h->n_sms = prop.multiProcessorCount;
     std::memset(&h->fluid, 0, sizeof(h->fluid));
     std::memset(&h->tab, 0, sizeof(h->tab));
-    if (cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {
+    if ((e = cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreate(&h->ev0)) != cudaSuccess || (e = cudaEventCreate(&h->ev1)) != cudaSuccess) {
         delete h;
-        return fail(nullptr, EU_ERR_CUDA, "stream/event creation failed");
+        return fail(nullptr, EU_ERR_CUDA, std::string("stream/event creation failed: ") + cudaGetErrorString(e));
     }
     *out = h;
     return EU_OK;
@@ -803,13 +982,21 @@ int eu_grid_end(eu_handle h)
         EU_CUDA(h, cudaMemcpyAsync(nreg, h->d_flags.p, sizeof(nreg), cudaMemcpyDeviceToHost, h->st));
         EU_CUDA(h, cudaStreamSynchronize(h->st));
         h->regular_fraction = rec_total > 0 ? double(nreg[1])/double(rec_total/EU_SLICE) : 0.0;
-        const size_t F = size_t(std::max<long long>(h->F, 1));
-        EU_CUDA(h, h->d_q.alloc(F));
-        EU_CUDA(h, h->d_G.alloc(F));
+        h->h_slice_base = base;
+        h->items_lo = h->items_hi = -1;
+        // one extra face (id F) with zero flux, G and T: the dummy face of the explicit slots of a slice class
+        const size_t F = size_t(std::max<long long>(h->F, 1)) + 1;
+        EU_CUDA(h, h->d_qg.alloc(F));
         EU_CUDA(h, h->d_T.alloc(F));
+        EU_CUDA(h, cudaMemsetAsync(h->d_qg.p, 0, F*sizeof(double2), h->st));
+        EU_CUDA(h, cudaMemsetAsync(h->d_T.p, 0, F*sizeof(double), h->st));
         EU_CUDA(h, h->d_pcscale.alloc(n));
         EU_CUDA(h, h->d_rock8.alloc(n));
         EU_CUDA(h, h->d_inv_porevol.alloc(n));
+        for (int k = 0; k < 2; ++k) {
+            EU_CUDA(h, h->d_lam[k].alloc(n));
+            EU_CUDA(h, cudaMemsetAsync(h->d_lam[k].p, 0, n*sizeof(double2), h->st));
+        }
         eu_launch_pcscale(g, h->tab, h->d_pcscale.p, h->d_rock8.p, h->d_inv_porevol.p, h->st);
         EU_CUDA(h, cudaStreamSynchronize(h->st));
     }
@@ -897,14 +1084,15 @@ int eu_small_step(eu_handle h, double dt, const double gravity[3], int n_src, co
     if ((rc = ensure_contracted(h, gravity))) return rc;
     const unsigned long long none = ~0ULL;
     EU_CUDA(h, cudaMemcpyAsync(h->d_fail_key.p, &none, sizeof(none), cudaMemcpyHostToDevice, h->st));
-    if (h->mode == EU_MODE_FAST && h->par.method_capillary)
-        eu_launch_fast_pc(h->grid(), h->tab, h->fast(), h->d_S[h->cur].p, h->d_pc[h->cur].p, 0, h->n_local, h->st);
+    if (h->mode == EU_MODE_FAST)
+        eu_launch_fast_state(h->grid(), h->tab, h->fast(), h->d_S[h->cur].p, h->par.method_capillary ? h->d_pc[h->cur].p : nullptr,
+                             h->d_lam[h->cur].p, 0, h->n_local, h->st);
     EuStepArgs a = step_args(h, dt, gravity, nls, 0);
     a.residual_out = h->d_residual.p;
     // ghost entries of the new state keep the old values (single substep, no exchange)
     EU_CUDA(h, cudaMemcpyAsync(h->d_S[h->cur ^ 1].p, h->d_S[h->cur].p, size_t(h->n_local)*sizeof(double), cudaMemcpyDeviceToDevice, h->st));
     if (h->cfg.world_size > 1) return fail(h, EU_ERR_UNSUPPORTED, "eu_small_step is a single-rank debugging entry point");
-    launch_substep(h, a, false);
+    if (launch_substep(h, a, false) < 0) return EU_ERR_CUDA;
     h->cur ^= 1;
     unsigned long long key = none;
     EU_CUDA(h, cudaMemcpyAsync(&key, h->d_fail_key.p, sizeof(key), cudaMemcpyDeviceToHost, h->st));
@@ -978,15 +1166,23 @@ int eu_transport_solve_resident(eu_handle h, double time, const double gravity[3
     while (!finished) {
         ++rep->attempts;
         EU_CUDA(h, cudaMemcpyAsync(h->d_fail_key.p, &none, sizeof(none), cudaMemcpyHostToDevice, h->st));
-        if (h->mode == EU_MODE_FAST && p.method_capillary) {
-            eu_launch_fast_pc(h->grid(), h->tab, h->fast(), h->d_S[h->cur].p, h->d_pc[h->cur].p, 0, h->n_local, h->st);
+        if (h->mode == EU_MODE_FAST) {
+            eu_launch_fast_state(h->grid(), h->tab, h->fast(), h->d_S[h->cur].p, p.method_capillary ? h->d_pc[h->cur].p : nullptr,
+                                 h->d_lam[h->cur].p, 0, h->n_local, h->st);
             ++launches;
         }
         const int start = h->cur;
+        if (h->mode == EU_MODE_FAST) {       // work items of the substep kernel (built once per grid / decomposition)
+            const bool fused = fused_halo(h);
+            if ((rc = build_items(h, fused ? h->fused_a_hi : h->own_lo/EU_SLICE,
+                                  fused ? h->fused_b_lo : (h->own_hi + EU_SLICE - 1)/EU_SLICE))) return rc;
+        }
         EU_CUDA(h, cudaEventRecord(h->ev0, h->st));
         for (int q = 0; q < nsteps; ++q) {
             EuStepArgs a = step_args(h, dt, gravity, nls, q);
-            launches += launch_substep(h, a, true);
+            const int nl = launch_substep(h, a, true);
+            if (nl < 0) return EU_ERR_CUDA;
+            launches += nl;
             if ((rc = halo_exchange(h, h->cur ^ 1, h->mode == EU_MODE_FAST && p.method_capillary, &launches))) return rc;
             h->cur ^= 1;
         }

@@ -87,6 +87,23 @@ struct Mob {
             lo = (1.0 - sat)*(1.0 - sat)*t.inv_visc[1];
         }
     }
+    // mobilities and capillary pressure at the same point: one interval search
+    static __device__ __forceinline__ void both_and_pc(const TabLayout& L, const EuTablesDev& t, int rock, double sat, double scale,
+                                                       double& lw, double& lo, double& pcv)
+    {
+        if (ROCKS) {
+            const int j = interval<MULTIROCK>(L, rock, sat);
+            const double4 c = L.coef()[j];
+            const double2 cj = L.jcoef()[j];
+            lw = fma(c.y, sat, c.x);
+            lo = fma(c.w, sat, c.z);
+            pcv = fma(cj.y, sat, cj.x)*scale;
+        } else {
+            lw = sat*sat*t.inv_visc[0];
+            lo = (1.0 - sat)*(1.0 - sat)*t.inv_visc[1];
+            pcv = 1e5*(1.0 - sat);
+        }
+    }
     static __device__ __forceinline__ double pc(const TabLayout& L, int rock, double sat, double scale)
     {
         if (ROCKS) {
@@ -98,24 +115,24 @@ struct Mob {
     }
 };
 
-// x/d for a positive, normal-range denominator (sum of two mobilities): reciprocal seed + two Newton
-// steps + one residual correction; no special-case branch.  Relative error <= 2^-52.
+// x/d for a positive, normal-range denominator (sum of two mobilities): reciprocal seed (>= 19 good bits), one
+// Newton step (>= 38 bits) and a residual correction of the quotient, which squares the error once more
+// (2^-76 + one rounding); no special-case branch.
 __device__ __forceinline__ double div_pos(double x, double d)
 {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
-    double e = fma(-d, r, 1.0);
+    const double e = fma(-d, r, 1.0);
     r = fma(r, e, r);
-    e = fma(-d, r, 1.0);
-    r = fma(r, e, r);
-    double qv = x*r;
+    const double qv = x*r;
     const double rem = fma(-d, qv, x);
     return fma(rem, r, qv);
 }
 
 // One face of the gather, from the point of view of cell "self" (mobilities lw0/lo0) against the cell or
 // boundary value on the other side (lw1/lo1).  own: self is the lower-index ("lo") cell, whose frame q, G
-// and T are expressed in.  Returns the contribution to residual[self].
+// and T are expressed in.  Returns the contribution to residual[self].  Everything decided at run time:
+// used for the slots read from SELL records (boundaries, faults, irregular slices).
 template <bool CAP>
 __device__ __forceinline__ double face_contribution(bool own, bool interior, double q, double qq, double G,
                                                     double lw0, double lo0, double lw1, double lo1,
@@ -129,22 +146,62 @@ __device__ __forceinline__ double face_contribution(bool own, bool interior, dou
     const double n0 = triv_w ? lo0 : lw0, n1 = triv_w ? lo1 : lw1;
     const bool u_self = (q >= 0.0) == own;                 // upstream cell of the trivial phase is self
     const double lam_t = u_self ? t0 : t1;
-    const double gfn = triv_w ? -(lam_t*G) : lam_t*G;
-    const bool u2_self = ((q + gfn) >= 0.0) == own;
+    const bool u2_self = (fma(lam_t, -fabs(G), q) >= 0.0) == own;
     const double lam_n = u2_self ? n0 : n1;
     const double lw = triv_w ? lam_t : lam_n;
-    const double lo = triv_w ? lam_n : lam_t;
-    double num = method_viscous ? qq : 0.0;
-    num = (method_gravity && interior) ? fma(lo, G, num) : num;
-    double dS = div_pos(lw*num, lam_t + lam_n);
+    // lam_w (q + lam_o G)/(lam_w + lam_o), the gravity part only on interior / periodic faces
+    double num = method_viscous ? lw*qq : 0.0;
+    num = (method_gravity && interior) ? fma(lam_t*lam_n, G, num) : num;
+    double dS = div_pos(num, lam_t + lam_n);
     if (CAP) dS = interior ? fma(cap_coef, Tdpc, dS) : dS;
     return own ? -dS : dS;
+}
+
+// The same face when the slot is regular: interior, and whether self is the lo cell is a compile-time
+// property of the slot (odd slots of a slice class hold the positive offsets).  Returns dS in the lo cell's
+// frame: the contribution is -dS to the lo cell and +dS to the hi cell.  G is zero when gravity is off.
+template <bool OWN, bool CAP>
+__device__ __forceinline__ double face_regular(double q, double qq, double G, double lw0, double lo0, double lw1, double lo1,
+                                               int method_viscous, double cap_coef, double Tdpc)
+{
+    const double lwa = OWN ? lw0 : lw1, lwb = OWN ? lw1 : lw0;      // a = lo cell, b = hi cell
+    const double loa = OWN ? lo0 : lo1, lob = OWN ? lo1 : lo0;
+    const bool triv_w = G >= 0.0;
+    const bool up_a = q >= 0.0;
+    const double cw = up_a ? lwa : lwb, co = up_a ? loa : lob;
+    const double lam_t = triv_w ? cw : co;
+    const bool up2 = fma(lam_t, -fabs(G), q) >= 0.0;
+    const double oa = triv_w ? loa : lwa, ob = triv_w ? lob : lwb;
+    const double lam_n = up2 ? oa : ob;
+    const double lw = triv_w ? lam_t : lam_n;
+    double num = lw*qq;
+    if (!method_viscous) num = 0.0;
+    num = fma(lam_t*lam_n, G, num);
+    double dS = div_pos(num, lam_t + lam_n);
+    if (CAP) dS = fma(cap_coef, Tdpc, dS);
+    return dS;
+}
+
+template <bool ROCKS, bool MULTIROCK>
+__device__ __forceinline__ double cap_coefficient(const TabLayout& L, const EuTablesDev& t, int rock0, int rock1, double S0, double S1)
+{
+    const double Sa = 0.5*(S0 + S1);
+    double lwa, loa;
+    Mob<ROCKS, MULTIROCK>::both(L, t, rock0, Sa, lwa, loa);
+    if (MULTIROCK && rock1 != rock0) {
+        double lwb, lob;
+        Mob<ROCKS, MULTIROCK>::both(L, t, rock1, Sa, lwb, lob);
+        lwa = 0.5*(lwa + lwb);
+        loa = 0.5*(loa + lob);
+    }
+    return div_pos(lwa*loa, lwa + loa);
 }
 
 template <bool ROCKS, bool MULTIROCK, bool CAP, bool NN, int W, int B>
 __device__ __forceinline__ double gather_cell(const TabLayout& L, const EuGridDev& g, const EuTablesDev& t,
                                               const EuFastDev& f, const EuStepArgs& a, const int2* __restrict__ recp,
-                                              const int2* __restrict__ dscp, int width, int c, double S0, int rock0, double pc0)
+                                              const int2* __restrict__ dscp, int width, int c, double S0, int rock0, double pc0,
+                                              double lw0, double lo0)
 {
     // phase A: the cell's records.  Regular slots come from the 8-byte slice descriptor (neighbour = c + d,
     // face id affine in c): no per-cell record is read; irregular slots (boundaries, faults) load theirs.
@@ -167,24 +224,22 @@ __device__ __forceinline__ double gather_cell(const TabLayout& L, const EuGridDe
         for (int j = 0; j < W; ++j)
             if (j < width && dsc[j].y == -1) r[j] = __ldg(recp + j*EU_SLICE);
     }
-    double lw0, lo0;
-    Mob<ROCKS, MULTIROCK>::both(L, t, rock0, S0, lw0, lo0);
     double acc = 0.0;
 #pragma unroll
     for (int j0 = 0; j0 < W; j0 += B) {
         // phase B: every gather of the batch in flight at once
-        double S1[B], q[B], G[B], T[CAP ? B : 1], pc1[CAP ? B : 1], nn[NN ? B : 1];
+        double S1[B], T[CAP ? B : 1], pc1[CAP ? B : 1], nn[NN ? B : 1];
+        double2 qg[B];
         int rk[MULTIROCK ? B : 1];
 #pragma unroll
         for (int k = 0; k < B; ++k) {
             const int j = j0 + k;
-            S1[k] = 0.0; q[k] = 0.0; G[k] = 0.0;
+            S1[k] = 0.0; qg[k] = make_double2(0.0, 0.0);
             if (CAP) { T[k] = 0.0; pc1[k] = 0.0; }
             if (NN) nn[k] = 1.0;
             if (MULTIROCK) rk[k] = rock0;
             if (j < W && r[j].x != EU_REC_PAD) {
-                q[k] = __ldg(f.q + r[j].y);
-                G[k] = __ldg(f.G + r[j].y);
+                qg[k] = __ldg(f.qg + r[j].y);
                 if (NN) nn[k] = __ldg(f.nn + r[j].y);
                 if (r[j].x >= 0) {
                     S1[k] = __ldg(a.S_in + r[j].x);
@@ -208,41 +263,34 @@ __device__ __forceinline__ double gather_cell(const TabLayout& L, const EuGridDe
             Mob<ROCKS, MULTIROCK>::both(L, t, rk1, S1[k], lw1, lo1);
             double cap_coef = 0.0, Tdpc = 0.0;
             if (CAP) {
-                const double Sa = 0.5*(S0 + S1[k]);
-                double lwa, loa;
-                Mob<ROCKS, MULTIROCK>::both(L, t, rock0, Sa, lwa, loa);
-                if (MULTIROCK && rk1 != rock0) {
-                    double lwb, lob;
-                    Mob<ROCKS, MULTIROCK>::both(L, t, rk1, Sa, lwb, lob);
-                    lwa = 0.5*(lwa + lwb);
-                    loa = 0.5*(loa + lob);
-                }
-                cap_coef = div_pos(lwa*loa, lwa + loa);
+                cap_coef = cap_coefficient<ROCKS, MULTIROCK>(L, t, rock0, rk1, S0, S1[k]);
                 Tdpc = T[k]*(own ? (pc1[k] - pc0) : (pc0 - pc1[k]));
             }
-            const double contrib = face_contribution<CAP>(own, interior, q[k], NN ? q[k]*nn[k] : q[k], G[k], lw0, lo0, lw1, lo1,
-                                                          a.method_viscous, a.method_gravity, cap_coef, Tdpc);
+            const double contrib = face_contribution<CAP>(own, interior, qg[k].x, NN ? qg[k].x*nn[k] : qg[k].x, qg[k].y, lw0, lo0,
+                                                          lw1, lo1, a.method_viscous, a.method_gravity, cap_coef, Tdpc);
             acc += valid ? contrib : 0.0;
         }
     }
     return acc;
 }
 
-// generic width (cells with more than 8 faces): same arithmetic, one face at a time
+// One face at a time from the SELL records: cells with more than 8 faces (slot_mask = all), and the explicit
+// slots of a slice class (slot_mask = those slots).  Same arithmetic as gather_cell.
 template <bool ROCKS, bool MULTIROCK, bool CAP, bool NN>
-__device__ double gather_cell_loop(const TabLayout& L, const EuGridDev& g, const EuTablesDev& t,
-                                   const EuFastDev& f, const EuStepArgs& a, const int2* __restrict__ recp,
-                                   int width, int c, double S0, int rock0, double pc0)
+__device__ __noinline__ double gather_cell_loop(const TabLayout& L, const EuGridDev& g, const EuTablesDev& t,
+                                                const EuFastDev& f, const EuStepArgs& a, const int2* __restrict__ recp,
+                                                int width, unsigned slot_mask, int c, double S0, int rock0, double pc0,
+                                                double lw0, double lo0)
 {
-    double lw0, lo0;
-    Mob<ROCKS, MULTIROCK>::both(L, t, rock0, S0, lw0, lo0);
     double acc = 0.0;
     for (int j = 0; j < width; ++j) {
+        if (j < 32 && !((slot_mask >> j) & 1u)) continue;
         const int2 r = recp[j*EU_SLICE];
         if (r.x == EU_REC_PAD) continue;
         const bool interior = r.x >= 0;
         const bool own = !interior || c < r.x;
-        const double q = f.q[r.y], G = f.G[r.y];
+        const double2 qg = f.qg[r.y];
+        const double q = qg.x, G = qg.y;
         const double nn = NN ? f.nn[r.y] : 1.0;
         const double S1 = interior ? a.S_in[r.x] : g.bnd_sat[-2 - r.x];
         const int rk = (MULTIROCK && interior) ? f.rock8[r.x] : rock0;
@@ -250,16 +298,7 @@ __device__ double gather_cell_loop(const TabLayout& L, const EuGridDev& g, const
         Mob<ROCKS, MULTIROCK>::both(L, t, rk, S1, lw1, lo1);
         double cap_coef = 0.0, Tdpc = 0.0;
         if (CAP && interior) {
-            const double Sa = 0.5*(S0 + S1);
-            double lwa, loa;
-            Mob<ROCKS, MULTIROCK>::both(L, t, rock0, Sa, lwa, loa);
-            if (MULTIROCK && rk != rock0) {
-                double lwb, lob;
-                Mob<ROCKS, MULTIROCK>::both(L, t, rk, Sa, lwb, lob);
-                lwa = 0.5*(lwa + lwb);
-                loa = 0.5*(loa + lob);
-            }
-            cap_coef = div_pos(lwa*loa, lwa + loa);
+            cap_coef = cap_coefficient<ROCKS, MULTIROCK>(L, t, rock0, rk, S0, S1);
             const double pc1 = a.pc_in[r.x];
             Tdpc = f.T[r.y]*(own ? (pc1 - pc0) : (pc0 - pc1));
         }
@@ -269,53 +308,193 @@ __device__ double gather_cell_loop(const TabLayout& L, const EuGridDev& g, const
     return acc;
 }
 
-template <bool ROCKS, bool MULTIROCK, bool CAP, bool NN, int B6, int B8, int MINB>
-__global__ void __launch_bounds__(kBlock, MINB) k_fast_step(EuGridDev g, EuTablesDev t, EuFastDev f, EuStepArgs a,
-                                                            EuHaloDev halo, int slice_lo, int slice_hi)
+// source term (:293-299), explicit update (EulerUpstream_impl.hpp:371-374), range check / clamp (:336-349) and the
+// capillary pressure of the new state (Residual_impl.hpp:459-467, fused); returns the new saturation
+template <bool ROCKS, bool MULTIROCK, bool CAP>
+__device__ __forceinline__ double finish_cell(const TabLayout& L, const EuTablesDev& t, const EuFastDev& f, const EuStepArgs& a,
+                                              int c, double S0, int rock0, double lw0, double lo0, double inv_pv, double acc,
+                                              double& pcn)
 {
-    TabLayout L;
-    L.nn = t.n_nodes_total; L.nb = t.n_buckets; L.shift = 0;
-    if (ROCKS) {
-        tables_to_smem(t);
-        __syncthreads();
+    if (a.n_src > 0) {
+        double rate = 0.0;
+        int lo = 0, hi = a.n_src;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (a.src_cell[mid] < c) lo = mid + 1; else hi = mid; }
+        if (lo < a.n_src && a.src_cell[lo] == c) rate = a.src_rate[lo];
+        if (rate < 0.0) rate *= lw0/(lw0 + lo0);
+        acc += rate;
     }
-    if (!halo.enabled) {   // (with a halo exchange every rank keeps stepping so that the flags stay in lockstep)
-        const unsigned long long key = *a.fail_key;
-        if (key != ~0ULL && (unsigned)(key >> 32) < (unsigned)a.substep) return;
-    }
-    const int lane = threadIdx.x & 31;
-    const int warp_global = blockIdx.x*kWarpsPerBlock + (threadIdx.x >> 5);
-    const int n_warps = gridDim.x*kWarpsPerBlock;
-    // processing order: boundary range A, boundary range B, then the interior
-    const int nA = halo.enabled ? halo.a_hi - slice_lo : 0;
-    const int nB = halo.enabled ? slice_hi - halo.b_lo : 0;
-    bool waited = false;
-
-    for (int v = warp_global; v < slice_hi - slice_lo; v += n_warps) {
-        int s, range = -1;
-        if (v < nA)           { s = slice_lo + v; range = 0; }
-        else if (v < nA + nB) { s = halo.b_lo + (v - nA); range = 1; }
-        else                  { s = slice_lo + nA + (v - nA - nB); }
-        if (range >= 0 && !waited) {
-            // ghosts of the previous substep must have landed before a boundary slice reads them
-            if (lane < halo.n_wait) {
-                const volatile unsigned* fl = halo.my_flags + halo.wait_rank[lane];
-                const long long t0 = clock64();
-                while ((int)(*fl - (halo.epoch - 1u)) < 0) {
-                    __nanosleep(100);
-                    if (clock64() - t0 > halo.timeout_cycles) { atomicExch(halo.err_flag, 1); break; }
-                }
-                __threadfence_system();
+    if (a.residual_out) a.residual_out[c] = acc;
+    double sat = fma(a.dt*acc, inv_pv, S0);
+    if (a.check_sat || a.clamp_sat) {
+        if (sat > 1.0 || sat < 0.0) {
+            if (a.clamp_sat) {
+                sat = fmax(fmin(sat, 1.0), 0.0);
+            } else if (sat > 1.001 || sat < -0.001) {
+                atomicMin(a.fail_key, ((unsigned long long)(unsigned)a.substep << 32) | (unsigned)c);
             }
-            __syncwarp();
-            waited = true;
         }
-        const int c = s*EU_SLICE + lane;
-        const bool active = (c >= g.own_lo) && (c < g.own_hi);
+    }
+    a.S_out[c] = sat;
+    // mobilities (and capillary pressure) of the new state, looked up once per cell: the marches of the next substep
+    // read their neighbours' mobilities instead of evaluating the rock curves again
+    double lwn, lon;
+    pcn = 0.0;
+    if (CAP) {
+        Mob<ROCKS, MULTIROCK>::both_and_pc(L, t, rock0, sat, ROCKS ? f.pcscale[c] : 1.0, lwn, lon, pcn);
+        a.pc_out[c] = pcn;
+    } else {
+        Mob<ROCKS, MULTIROCK>::both(L, t, rock0, sat, lwn, lon);
+    }
+    a.lam_out[c] = make_double2(lwn, lon);
+    return sat;
+}
+
+// ---- march along a slice class ---------------------------------------------------------------------------
+// A work item of a slice class is `len` slices s, s + D/32, ... of the same class (EuSliceClass in eu_internal.h).
+// Per cell the regular code evaluates slots 0..3 and 5; slot 4 only for the first cell of the march: afterwards it
+// is the previous cell's slot 5, carried in registers together with that neighbour's saturation, mobilities, rock
+// and capillary pressure.  The neighbours' mobilities come from the per-cell {lambda_w, lambda_o} pairs the previous
+// substep stored (finish_cell), so a step needs per face one 16-byte pair of the neighbour and one 16-byte {q, G}
+// pair of the face, all issued as one batch of loads before any arithmetic.
+__device__ __forceinline__ double2 ldg_pair(const double2* p)
+{
+    double2 v;
+    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double ldg_f64(const double* p)
+{
+    double v;
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
+// state carried along a march
+struct MarchCarry {
+    double S0, lw0, lo0, pc0, dS4;     // this cell; dS4 = flux of its slot-4 face in the lo cell's frame
+    int rock0;
+};
+
+// one regular face: capillary coefficient (if any) and dS in the lo cell's frame
+template <bool ROCKS, bool MULTIROCK, bool CAP, bool OWN>
+__device__ __forceinline__ double regular_slot(const TabLayout& L, const EuTablesDev& t, const EuStepArgs& a, const MarchCarry& m,
+                                               double2 lam1, double S1, int rk1, double2 qg, double nn, bool use_nn, double T,
+                                               double pc1)
+{
+    double cap_coef = 0.0, Tdpc = 0.0;
+    if (CAP) {
+        cap_coef = cap_coefficient<ROCKS, MULTIROCK>(L, t, m.rock0, rk1, m.S0, S1);
+        Tdpc = T*(OWN ? (pc1 - m.pc0) : (m.pc0 - pc1));
+    }
+    return face_regular<OWN, CAP>(qg.x, use_nn ? qg.x*nn : qg.x, qg.y, m.lw0, m.lo0, lam1.x, lam1.y, a.method_viscous, cap_coef, Tdpc);
+}
+
+// the first cell of a march: its own state and the slot-4 face
+template <bool ROCKS, bool MULTIROCK, bool CAP, bool NN>
+__device__ __forceinline__ void march_head(const TabLayout& L, const EuTablesDev& t, const EuFastDev& f, const EuStepArgs& a,
+                                           const EuSliceClass* __restrict__ cl, int c, MarchCarry& m)
+{
+    const int nb = c + cl->nb_off[4];
+    const int fid = c*cl->fid_mul[4] + cl->fid_off[4];
+    const double2 lam0 = ldg_pair(a.lam_in + c), lam1 = ldg_pair(a.lam_in + nb), qg = ldg_pair(f.qg + fid);
+    m.S0 = ldg_f64(a.S_in + c);
+    const double S1 = CAP ? __ldg(a.S_in + nb) : 0.0;
+    const double nn = NN ? __ldg(f.nn + fid) : 1.0;
+    m.rock0 = MULTIROCK ? __ldg(f.rock8 + c) : 0;
+    const int rk1 = (MULTIROCK && CAP) ? __ldg(f.rock8 + nb) : 0;
+    m.pc0 = CAP ? __ldg(a.pc_in + c) : 0.0;
+    const double T = CAP ? __ldg(f.T + fid) : 0.0, pc1 = CAP ? __ldg(a.pc_in + nb) : 0.0;
+    m.lw0 = lam0.x; m.lo0 = lam0.y;
+    m.dS4 = regular_slot<ROCKS, MULTIROCK, CAP, false>(L, t, a, m, lam1, S1, rk1, qg, nn, NN, T, pc1);
+}
+
+// one cell of a march; advances the carry to the cell across slot 5
+template <bool ROCKS, bool MULTIROCK, bool CAP, bool NN, bool RECORDS>
+__device__ __forceinline__ void march_step(const TabLayout& L, const EuGridDev& g, const EuTablesDev& t, const EuFastDev& f,
+                                           const EuStepArgs& a, const EuSliceClass* __restrict__ cl, int c, int lane, MarchCarry& m)
+{
+    constexpr int kOrder[5] = { 5, 3, 2, 1, 0 };       // far neighbours first: their lines take longest to arrive
+    int nb[6], fid[6];
+    double2 lam[6], qg[6];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const int j = kOrder[k];
+        nb[j] = c + cl->nb_off[j];
+        fid[j] = c*cl->fid_mul[j] + cl->fid_off[j];
+        lam[j] = ldg_pair(a.lam_in + nb[j]);
+        qg[j] = ldg_pair(f.qg + fid[j]);
+    }
+    const double S5 = ldg_f64(a.S_in + nb[5]);
+    const double inv_pv = ldg_f64(f.inv_porevol + c);
+    double S1[6], T[6], pc1[6], nn[6];
+    int rk[6];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const int j = kOrder[k];
+        S1[j] = (CAP && j != 5) ? __ldg(a.S_in + nb[j]) : S5;
+        rk[j] = (MULTIROCK && (CAP || j == 5)) ? __ldg(f.rock8 + nb[j]) : 0;
+        nn[j] = NN ? __ldg(f.nn + fid[j]) : 1.0;
+        T[j] = CAP ? __ldg(f.T + fid[j]) : 0.0;
+        pc1[j] = CAP ? __ldg(a.pc_in + nb[j]) : 0.0;
+    }
+    double acc = m.dS4;                 // self is the hi cell of the slot-4 face: +dS
+#ifdef EU_EXP_NOARITH               // timing experiment: the memory access pattern without the face arithmetic
+    m.dS4 = 0.0;
+    for (int k = 0; k < 5; ++k) { const int j = kOrder[k]; acc += 1e-30*(lam[j].x + lam[j].y + qg[j].x + qg[j].y); }
+    if (false)
+#endif
+    {
+    m.dS4 = regular_slot<ROCKS, MULTIROCK, CAP, true>(L, t, a, m, lam[5], S1[5], rk[5], qg[5], nn[5], NN, T[5], pc1[5]);
+    acc -= m.dS4;
+    acc -= regular_slot<ROCKS, MULTIROCK, CAP, true>(L, t, a, m, lam[3], S1[3], rk[3], qg[3], nn[3], NN, T[3], pc1[3]);
+    acc += regular_slot<ROCKS, MULTIROCK, CAP, false>(L, t, a, m, lam[2], S1[2], rk[2], qg[2], nn[2], NN, T[2], pc1[2]);
+    acc -= regular_slot<ROCKS, MULTIROCK, CAP, true>(L, t, a, m, lam[1], S1[1], rk[1], qg[1], nn[1], NN, T[1], pc1[1]);
+    acc += regular_slot<ROCKS, MULTIROCK, CAP, false>(L, t, a, m, lam[0], S1[0], rk[0], qg[0], nn[0], NN, T[0], pc1[0]);
+    }
+    if (RECORDS) {                      // boundary / fault faces of this class, from the SELL records
+        const int base = f.slice_base[c >> 5];
+        acc += gather_cell_loop<ROCKS, MULTIROCK, CAP, NN>(L, g, t, f, a, f.rec + base + lane, 6, (unsigned)cl->rec_mask, c, m.S0,
+                                                           m.rock0, m.pc0, m.lw0, m.lo0);
+    }
+    double pcn;
+    finish_cell<ROCKS, MULTIROCK, CAP>(L, t, f, a, c, m.S0, m.rock0, m.lw0, m.lo0, inv_pv, acc, pcn);
+    m.S0 = S5; m.lw0 = lam[5].x; m.lo0 = lam[5].y; m.rock0 = rk[5]; m.pc0 = pc1[5];
+}
+
+// Items of classes with explicit slots run the same march out of line, so that the call of the record loop does
+// not constrain the register allocation of the common path.
+template <bool ROCKS, bool MULTIROCK, bool CAP, bool NN, bool RECORDS>
+__device__ __forceinline__ void march_item_impl(const TabLayout& L, const EuGridDev& g, const EuTablesDev& t, const EuFastDev& f,
+                                                const EuStepArgs& a, const EuSliceClass* __restrict__ cl, int s, int len, int lane)
+{
+    int c = s*EU_SLICE + lane;
+    const int D = cl->D;
+    MarchCarry m;
+    march_head<ROCKS, MULTIROCK, CAP, NN>(L, t, f, a, cl, c, m);
+    for (int i = 0; i < len; ++i) {
+        march_step<ROCKS, MULTIROCK, CAP, NN, RECORDS>(L, g, t, f, a, cl, c, lane, m);
+        c += D;
+    }
+}
+template <bool ROCKS, bool MULTIROCK, bool CAP, bool NN>
+__device__ __noinline__ void march_item_records(const TabLayout& L, const EuGridDev& g, const EuTablesDev& t, const EuFastDev& f,
+                                                const EuStepArgs& a, const EuSliceClass* __restrict__ cl, int s, int len, int lane)
+{
+    march_item_impl<ROCKS, MULTIROCK, CAP, NN, true>(L, g, t, f, a, cl, s, len, lane);
+}
+
+// One slice through its descriptors / records: slices next to a slab boundary (with the halo push), slices that
+// straddle the own range, irregular slices (faults, cells with other than six faces).
+template <bool ROCKS, bool MULTIROCK, bool CAP, bool NN, int B6, int B8>
+__device__ __forceinline__ void slice_generic(const TabLayout& L, const EuGridDev& g, const EuTablesDev& t, const EuFastDev& f,
+                                              const EuStepArgs& a, const EuHaloDev& halo, int s, int range, int lane,
+                                              int slice_lo)
+{
+    const int c = s*EU_SLICE + lane;
+    const bool active = (c >= g.own_lo) && (c < g.own_hi);
+    if (active) {
         const int base = f.slice_base[s];
         const int width = (f.slice_base[s + 1] - base) >> 5;
-        if (!active && range < 0) continue;
-        if (active) {
         const double S0 = a.S_in[c];
         const int rock0 = MULTIROCK ? f.rock8[c] : 0;
         const double pc0 = CAP ? a.pc_in[c] : 0.0;
@@ -323,36 +502,13 @@ __global__ void __launch_bounds__(kBlock, MINB) k_fast_step(EuGridDev g, EuTable
         const int2* __restrict__ recp = f.rec + base + lane;
         const int2* __restrict__ dscp = f.desc + (base >> 5);
         double acc;
-        if (width <= 6)      acc = gather_cell<ROCKS, MULTIROCK, CAP, NN, 6, B6>(L, g, t, f, a, recp, dscp, width, c, S0, rock0, pc0);
-        else if (width <= 8) acc = gather_cell<ROCKS, MULTIROCK, CAP, NN, 8, B8>(L, g, t, f, a, recp, dscp, width, c, S0, rock0, pc0);
-        else                 acc = gather_cell_loop<ROCKS, MULTIROCK, CAP, NN>(L, g, t, f, a, recp, width, c, S0, rock0, pc0);
-
-        double rate = 0.0;
-        if (a.n_src > 0) {
-            int lo = 0, hi = a.n_src;
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (a.src_cell[mid] < c) lo = mid + 1; else hi = mid; }
-            if (lo < a.n_src && a.src_cell[lo] == c) rate = a.src_rate[lo];
-            if (rate < 0.0) {
-                double lw, lo_;
-                Mob<ROCKS, MULTIROCK>::both(L, t, rock0, S0, lw, lo_);
-                rate *= lw/(lw + lo_);
-            }
-        }
-        acc += rate;
-        if (a.residual_out) a.residual_out[c] = acc;
-        double sat = fma(a.dt*acc, inv_pv, S0);
-        if (a.check_sat || a.clamp_sat) {
-            if (sat > 1.0 || sat < 0.0) {
-                if (a.clamp_sat) {
-                    sat = fmax(fmin(sat, 1.0), 0.0);
-                } else if (sat > 1.001 || sat < -0.001) {
-                    atomicMin(a.fail_key, ((unsigned long long)(unsigned)a.substep << 32) | (unsigned)c);
-                }
-            }
-        }
-        a.S_out[c] = sat;
-        double pcn = 0.0;
-        if (CAP) { pcn = Mob<ROCKS, MULTIROCK>::pc(L, rock0, sat, ROCKS ? f.pcscale[c] : 1.0); a.pc_out[c] = pcn; }
+        double lw0, lo0;
+        Mob<ROCKS, MULTIROCK>::both(L, t, rock0, S0, lw0, lo0);
+        if (width <= 6)      acc = gather_cell<ROCKS, MULTIROCK, CAP, NN, 6, B6>(L, g, t, f, a, recp, dscp, width, c, S0, rock0, pc0, lw0, lo0);
+        else if (width <= 8) acc = gather_cell<ROCKS, MULTIROCK, CAP, NN, 8, B8>(L, g, t, f, a, recp, dscp, width, c, S0, rock0, pc0, lw0, lo0);
+        else                 acc = gather_cell_loop<ROCKS, MULTIROCK, CAP, NN>(L, g, t, f, a, recp, width, 0xffffffffu, c, S0, rock0, pc0, lw0, lo0);
+        double pcn;
+        const double sat = finish_cell<ROCKS, MULTIROCK, CAP>(L, t, f, a, c, S0, rock0, lw0, lo0, inv_pv, acc, pcn);
         if (range >= 0) {
             // this cell is a ghost of the neighbour rank: store it into the neighbour's HBM as well
             const int first = (range == 0 ? slice_lo : halo.b_lo)*EU_SLICE;
@@ -363,25 +519,95 @@ __global__ void __launch_bounds__(kBlock, MINB) k_fast_step(EuGridDev g, EuTable
             }
             __threadfence_system();
         }
-        }   // active
-        if (range >= 0) {
-            __syncwarp();
-            if (lane == 0) {
-                const unsigned done = atomicAdd(halo.counter[range], 1u);
-                if (done == halo.total[range] - 1u) {
-                    *halo.counter[range] = 0u;
-                    __threadfence_system();
-                    *(volatile unsigned*)halo.peer_flag[range] = halo.epoch;
-                    __threadfence_system();
-                }
+    }
+    if (range >= 0) {
+        __syncwarp();
+        if (lane == 0) {
+            const unsigned done = atomicAdd(halo.counter[range], 1u);
+            if (done == halo.total[range] - 1u) {
+                *halo.counter[range] = 0u;
+                __threadfence_system();
+                *(volatile unsigned*)halo.peer_flag[range] = halo.epoch;
+                __threadfence_system();
             }
         }
     }
 }
 
+// Persistent grid.  Processing order: the two slice ranges next to slab boundaries (multi-GPU runs; their results
+// are also pushed into the neighbours' ghost cells), then the work items of the interior, item v to warp v mod #warps.
+template <bool ROCKS, bool MULTIROCK, bool CAP, bool NN, int B6, int B8, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB) k_fast_step(EuGridDev g, EuTablesDev t, EuFastDev f, EuStepArgs a,
+                                                            EuHaloDev halo, int slice_lo, int slice_hi, int class_smem_offset)
+{
+    TabLayout L;
+    L.nn = t.n_nodes_total; L.nb = t.n_buckets; L.shift = 0;
+    if (ROCKS) tables_to_smem(t);
+    EuSliceClass* classes = reinterpret_cast<EuSliceClass*>(eu_smem + class_smem_offset);
+    {
+        const int n_words = f.n_classes*int(sizeof(EuSliceClass)/sizeof(int));
+        const int* src = reinterpret_cast<const int*>(f.classes);
+        int* dst = reinterpret_cast<int*>(classes);
+        for (int i = threadIdx.x; i < n_words; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    if (!halo.enabled) {   // (with a halo exchange every rank keeps stepping so that the flags stay in lockstep)
+        const unsigned long long key = *a.fail_key;
+        if (key != ~0ULL && (unsigned)(key >> 32) < (unsigned)a.substep) return;
+    }
+    const int lane = threadIdx.x & 31;
+    const int warp_global = blockIdx.x*kWarpsPerBlock + (threadIdx.x >> 5);
+    const int n_warps = gridDim.x*kWarpsPerBlock;
+    const int nAB = halo.enabled ? (halo.a_hi - slice_lo) + (slice_hi - halo.b_lo) : 0;
+    const int nA = halo.enabled ? halo.a_hi - slice_lo : 0;
+    int v = warp_global;
+    if (v < nAB) {
+        // ghosts of the previous substep must have landed before a boundary slice reads them
+        if (lane < halo.n_wait) {
+            const volatile unsigned* fl = halo.my_flags + halo.wait_rank[lane];
+            const long long t0 = clock64();
+            while ((int)(*fl - (halo.epoch - 1u)) < 0) {
+                __nanosleep(100);
+                if (clock64() - t0 > halo.timeout_cycles) { atomicExch(halo.err_flag, 1); break; }
+            }
+            __threadfence_system();
+        }
+        __syncwarp();
+        for (; v < nAB; v += n_warps) {
+            const int range = v < nA ? 0 : 1;
+            const int s = v < nA ? slice_lo + v : halo.b_lo + (v - nA);
+            slice_generic<ROCKS, MULTIROCK, CAP, NN, B6, B8>(L, g, t, f, a, halo, s, range, lane, slice_lo);
+        }
+    }
+    // ---- interior items
+    int vi = v - nAB;
+    if (vi >= f.n_items) return;
+    int2 item = __ldg(f.items + vi);
+    for (;;) {
+        // the next item of this warp is fetched before the current one is processed
+        const bool has_next = vi + n_warps < f.n_items;
+        int2 item_next = item;
+        if (has_next) item_next = __ldg(f.items + vi + n_warps);
+        const int cls = int(unsigned(item.y) >> 16);
+        if (cls == EU_ITEM_GENERIC) {
+            slice_generic<ROCKS, MULTIROCK, CAP, NN, B6, B8>(L, g, t, f, a, halo, item.x, -1, lane, slice_lo);
+        } else {
+            const EuSliceClass* cl = classes + cls;
+            if (cl->rec_mask != 0) march_item_records<ROCKS, MULTIROCK, CAP, NN>(L, g, t, f, a, cl, item.x, item.y & 0xffff, lane);
+            else                   march_item_impl<ROCKS, MULTIROCK, CAP, NN, false>(L, g, t, f, a, cl, item.x, item.y & 0xffff, lane);
+        }
+        if (!has_next) break;
+        item = item_next;
+        vi += n_warps;
+    }
+}
+
+// capillary pressure and mobilities of a given state (start of an attempt; afterwards the substep kernel keeps
+// them current for the cells it updates, and the halo exchange for the ghosts)
 template <bool ROCKS, bool MULTIROCK>
-__global__ void __launch_bounds__(kBlock) k_fast_pc(EuGridDev g, EuTablesDev t, EuFastDev f,
-                                                    const double* __restrict__ S, double* __restrict__ pc, int lo, int hi)
+__global__ void __launch_bounds__(kBlock) k_fast_state(EuGridDev g, EuTablesDev t, EuFastDev f,
+                                                       const double* __restrict__ S, double* __restrict__ pc,
+                                                       double2* __restrict__ lam, int lo, int hi)
 {
     TabLayout L;
     L.nn = t.n_nodes_total; L.nb = t.n_buckets; L.shift = 0;
@@ -390,7 +616,10 @@ __global__ void __launch_bounds__(kBlock) k_fast_pc(EuGridDev g, EuTablesDev t, 
         __syncthreads();
     }
     for (int c = lo + blockIdx.x*blockDim.x + threadIdx.x; c < hi; c += gridDim.x*blockDim.x) {
-        pc[c] = Mob<ROCKS, MULTIROCK>::pc(L, MULTIROCK ? f.rock8[c] : 0, S[c], ROCKS ? f.pcscale[c] : 1.0);
+        double lw, lo_, pcv;
+        Mob<ROCKS, MULTIROCK>::both_and_pc(L, t, MULTIROCK ? f.rock8[c] : 0, S[c], ROCKS ? f.pcscale[c] : 1.0, lw, lo_, pcv);
+        if (pc) pc[c] = pcv;
+        lam[c] = make_double2(lw, lo_);
     }
 }
 
@@ -403,38 +632,44 @@ size_t eu_fast_smem_bytes(const EuTablesDev& t)
     return (b + 15) & ~size_t(15);
 }
 
-void eu_launch_fast_pc(const EuGridDev& g, const EuTablesDev& t, const EuFastDev& f, const double* S, double* pc,
-                       int lo, int hi, cudaStream_t st)
+void eu_launch_fast_state(const EuGridDev& g, const EuTablesDev& t, const EuFastDev& f, const double* S, double* pc,
+                          double2* lam, int lo, int hi, cudaStream_t st)
 {
     if (hi <= lo) return;
     const size_t smem = eu_fast_smem_bytes(t);
     int blocks = (hi - lo + kBlock - 1)/kBlock;
     if (blocks > 148*8) blocks = 148*8;
-    if (t.n_rocks > 1)       k_fast_pc<true, true><<<blocks, kBlock, smem, st>>>(g, t, f, S, pc, lo, hi);
-    else if (t.n_rocks == 1) k_fast_pc<true, false><<<blocks, kBlock, smem, st>>>(g, t, f, S, pc, lo, hi);
-    else                     k_fast_pc<false, false><<<blocks, kBlock, 0, st>>>(g, t, f, S, pc, lo, hi);
+    if (t.n_rocks > 1)       k_fast_state<true, true><<<blocks, kBlock, smem, st>>>(g, t, f, S, pc, lam, lo, hi);
+    else if (t.n_rocks == 1) k_fast_state<true, false><<<blocks, kBlock, smem, st>>>(g, t, f, S, pc, lam, lo, hi);
+    else                     k_fast_state<false, false><<<blocks, kBlock, 0, st>>>(g, t, f, S, pc, lam, lo, hi);
 }
 
 template <bool ROCKS, bool MULTIROCK, bool CAP, bool NN, int B6, int B8, int MINB>
 static void launch_variant(const EuGridDev& g, const EuTablesDev& t, const EuFastDev& f, const EuStepArgs& a,
-                           const EuHaloDev& halo, int slice_lo, int slice_hi, int n_sms, size_t smem, cudaStream_t st)
+                           const EuHaloDev& halo, int slice_lo, int slice_hi, int n_sms, size_t smem_tables, cudaStream_t st)
 {
     static int blocks_per_sm = 0;
+    static size_t smem_seen = 0;
     auto kern = k_fast_step<ROCKS, MULTIROCK, CAP, NN, B6, B8, MINB>;
-    if (blocks_per_sm == 0) {
+    // shared memory: rock tables | slice classes
+    const size_t smem = smem_tables + sizeof(EuSliceClass)*EU_MAX_CLASSES;
+    if (blocks_per_sm == 0 || smem != smem_seen) {      // (another solver in this process may have larger tables)
         if (smem > 48*1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kBlock, smem);
         if (blocks_per_sm < 1) blocks_per_sm = 1;
+        smem_seen = smem;
     }
     // persistent grid: every SM full, capped by the work available
-    const int n = slice_hi - slice_lo;
+    int n = f.n_items;
+    if (halo.enabled) n += (halo.a_hi - slice_lo) + (slice_hi - halo.b_lo);
     int blocks = n_sms*blocks_per_sm;
     const int need = (n + kWarpsPerBlock - 1)/kWarpsPerBlock;
     if (blocks > need) blocks = need;
-    kern<<<blocks, kBlock, smem, st>>>(g, t, f, a, halo, slice_lo, slice_hi);
+    if (blocks < 1) return;
+    kern<<<blocks, kBlock, smem, st>>>(g, t, f, a, halo, slice_lo, slice_hi, (int)smem_tables);
 }
 
-// EU_FAST_VARIANT (tuning knob, read once): faces per load batch / resident blocks per SM
+// EU_FAST_VARIANT (tuning knob, read once): resident blocks per SM the kernel is compiled for
 static int fast_variant()
 {
     static int v = -1;
@@ -447,12 +682,9 @@ static void launch_fast(const EuGridDev& g, const EuTablesDev& t, const EuFastDe
                         const EuHaloDev& halo, int slice_lo, int slice_hi, int n_sms, size_t smem, cudaStream_t st)
 {
     switch (fast_variant()) {
-    case 1:  launch_variant<ROCKS, MULTIROCK, CAP, NN, 3, 4, 5>(g, t, f, a, halo, slice_lo, slice_hi, n_sms, smem, st); break;
-    case 2:  launch_variant<ROCKS, MULTIROCK, CAP, NN, 2, 2, 5>(g, t, f, a, halo, slice_lo, slice_hi, n_sms, smem, st); break;
-    case 3:  launch_variant<ROCKS, MULTIROCK, CAP, NN, 2, 2, 6>(g, t, f, a, halo, slice_lo, slice_hi, n_sms, smem, st); break;
-    case 4:  launch_variant<ROCKS, MULTIROCK, CAP, NN, 1, 1, 6>(g, t, f, a, halo, slice_lo, slice_hi, n_sms, smem, st); break;
-    case 5:  launch_variant<ROCKS, MULTIROCK, CAP, NN, 1, 1, 8>(g, t, f, a, halo, slice_lo, slice_hi, n_sms, smem, st); break;
-    default: launch_variant<ROCKS, MULTIROCK, CAP, NN, 3, 4, 4>(g, t, f, a, halo, slice_lo, slice_hi, n_sms, smem, st); break;
+    case 1:  launch_variant<ROCKS, MULTIROCK, CAP, NN, 3, 4, 2>(g, t, f, a, halo, slice_lo, slice_hi, n_sms, smem, st); break;
+    case 2:  launch_variant<ROCKS, MULTIROCK, CAP, NN, 3, 4, 4>(g, t, f, a, halo, slice_lo, slice_hi, n_sms, smem, st); break;
+    default: launch_variant<ROCKS, MULTIROCK, CAP, NN, 3, 4, 3>(g, t, f, a, halo, slice_lo, slice_hi, n_sms, smem, st); break;
     }
 }
 

@@ -83,16 +83,39 @@ struct EuStrictDev {
     const double* porevol;    // volume*poro
 };
 
+// Slice classes (FAST mode).  A slice of 32 own cells whose regular slots come in (-d, +d) pairs belongs to a
+// class: the per-slot neighbour / face offsets are the same for every slice of the class, so the kernel keeps them
+// in shared memory and never reads the slice's descriptors.  Slots are reordered so that slot 2p is the negative and
+// slot 2p+1 the positive offset of pair p, and the pair with the largest offset that is a whole number of slices sits
+// in slots 4/5: the kernel *marches* along it (slice s, s + D/32, ...), carrying the flux of face 5 of one cell over
+// as face 4 of the next (the same face, evaluated once), together with the neighbour's saturation and mobilities.
+// Slots that are not regular in this class (boundary faces, fault faces) are explicit: the regular code runs on a
+// dummy face with zero flux for them (face id F, one past the real faces) and the real face is added from the slice's
+// SELL records afterwards.
+#define EU_MAX_CLASSES 40
+#define EU_ITEM_GENERIC 0xffff
+struct EuSliceClass {
+    int nb_off[6];            // regular slot: neighbour = cell + nb_off;  explicit: 0
+    int fid_mul[6];           // regular slot: face = cell*1 + fid_off;    explicit: cell*0 + (the all-zero face F)
+    int fid_off[6];
+    int D;                    // march stride in cells (multiple of 32); 0 = items of this class have length 1
+    int rec_mask;             // bit j: slot j of the SELL records is an explicit face of this class
+    int pad[2];
+};
+
 struct EuFastDev {
     int n_slices;             // slices over all local cells
     int n_local;              // face id = plane*n_local + owner cell, plane = the owner's local face slot
+    const int2* items;        // work items of the interior slice range: {first slice, length | class << 16}
+    int n_items;
+    const EuSliceClass* classes;   // n_classes <= EU_MAX_CLASSES
+    int n_classes;
     const int* slice_base;    // n_slices+1, record offsets (multiples of 32)
     const int2* rec;          // explicit records, read only for the slots a descriptor marks irregular
     const int2* desc;         // per (slice, slot) at slice_base/32 + slot: {d, k}.  k >= 0: every lane's neighbour
                               // is cell + d and its face lives in plane k (regular slot, no record needed);
                               // k == -1: irregular slot, use rec; k == -2: no face in this slot
-    const double* q;          // compacted flux of the current transportSolve
-    const double* G;
+    const double2* qg;        // per unique face {q, G}: compacted flux of the current transportSolve, gravity scalar
     const double* T;
     const double* nn;         // n.n per face, or NULL when all normals are unit to 1e-13
     const double* inv_porevol;   // 1/(volume*poro)
@@ -113,6 +136,8 @@ struct EuStepArgs {
     double* S_out;
     const double* pc_in;      // FAST: pc(S_in) for all local cells; STRICT: scratch filled by k_strict_pc
     double* pc_out;
+    const double2* lam_in;    // FAST: {lambda_w, lambda_o}(S_in) of the own cells (the marches read their neighbours' pairs)
+    double2* lam_out;
     double* residual_out;     // optional
     unsigned long long* fail_key;   // min over failing (substep<<32 | local cell)
     double gravity[3];
@@ -174,8 +199,8 @@ void eu_launch_halo_push(const int* send_src, const int* send_dst, int n, const 
 void eu_launch_halo_wait(const unsigned* my_flags, const int* wait_ranks, int n_wait, unsigned epoch,
                          long long timeout_cycles, int* err_flag, cudaStream_t st);
 // ---- eu_fast.cu ------------------------------------------------------------------------------
-void eu_launch_fast_pc(const EuGridDev& g, const EuTablesDev& t, const EuFastDev& f, const double* S, double* pc,
-                       int lo, int hi, cudaStream_t st);
+void eu_launch_fast_state(const EuGridDev& g, const EuTablesDev& t, const EuFastDev& f, const double* S, double* pc,
+                          double2* lam, int lo, int hi, cudaStream_t st);
 void eu_launch_fast_step(const EuGridDev& g, const EuTablesDev& t, const EuFastDev& f, const EuStepArgs& a,
                          const EuHaloDev& halo, int slice_lo, int slice_hi, int n_sms, cudaStream_t st);
 void eu_launch_ghost_adjacent(const EuGridDev& g, int* out4, cudaStream_t st);

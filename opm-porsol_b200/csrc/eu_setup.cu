@@ -240,7 +240,7 @@ __global__ void k_contract(EuGridDev g, EuTablesDev t, const int* __restrict__ o
         for (int i = 0; i < 3; ++i) gi[i] *= t.delta_rho;
         const double area = g.hf_area[h];
         const double nrm[3] = { g.hf_normal[3LL*h], g.hf_normal[3LL*h + 1], g.hf_normal[3LL*h + 2] };
-        G[fid] = method_gravity ? area*sm_inner3(nrm, gi) : 0.0;
+        G[2LL*fid] = method_gravity ? area*sm_inner3(nrm, gi) : 0.0;       // interleaved {q, G} pairs
         double Tv = 0.0;
         if (interior_like) {
             double dirhat[3], d0d1, ci[3];
@@ -321,7 +321,7 @@ __global__ void k_cfl_velocity_compact(EuGridDev g, double cfl_factor, const dou
         for (int h = b; h < e; ++h) {
             const double f = hf_flux[h];
             if (f > 0) flux_p += f; else flux_n -= f;
-            if (q) { const int fid = fid_of_hf[h]; if (fid >= 0) q[fid] = f; }
+            if (q) { const int fid = fid_of_hf[h]; if (fid >= 0) q[2LL*fid] = f; }      // interleaved {q, G} pairs
         }
         if (c >= g.own_lo && c < g.own_hi) {
             const double flux = flux_n > flux_p ? flux_n : flux_p;         // std::max(flux_n, flux_p)

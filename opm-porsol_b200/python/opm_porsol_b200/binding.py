@@ -79,6 +79,9 @@ class Report:
 
 def lib_path() -> str:
     here = os.path.dirname(os.path.abspath(__file__))
+    override = os.environ.get("EU_B200_LIB")           # kernel experiments: another build of the same library
+    if override:
+        return override
     return os.path.normpath(os.path.join(here, "..", "..", "lib", "libeuler_b200.so"))
 
 
