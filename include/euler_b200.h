@@ -198,6 +198,34 @@ int eu_small_step(eu_handle h, double dt, const double gravity[3],
                   int n_src, const int* src_cell, const double* src_rate,
                   double* residual_out, int* bad_cell, double* bad_value);
 
+/* ---- the residual as an operator: EulerUpstreamResidual::computeResidual(saturation, gravity, flow_sol,
+ *      injection_rates, method_viscous, method_gravity, method_capillary, sat_delta)
+ *      (EulerUpstreamResidual.hpp:83-91, _impl.hpp:472-505).  Second caller in the reference:
+ *      ImplicitCapillarity::transportSolve (ImplicitCapillarity_impl.hpp:178-180, capillary = false).
+ * saturation: all local cells (host); hf_flux: all local half-faces (host), or NULL to reuse the fluxes already
+ * resident from eu_upload_state / the last eu_transport_solve; sat_delta: the own cells (host, out).
+ * The method flags are arguments, as in the reference; the solver's eu_params are not consulted or changed,
+ * nor is the resident saturation. */
+int eu_compute_residual(eu_handle h, const double* saturation, const double gravity[3], const double* hf_flux,
+                        int n_src, const int* src_cell, const double* src_rate,
+                        int method_viscous, int method_gravity, int method_capillary, double* sat_delta);
+/* EulerUpstreamResidual::computeCapPressures (:459-467): pc[c] = rp.capillaryPressure(c, saturation[c]) for all
+ * local cells, reference operation order (bit-identical in every mode). */
+int eu_compute_cap_pressures(eu_handle h, const double* saturation, double* cap_pressures);
+
+/* ---- diagnostics on resident data, the per-cell / per-face loops the drivers run right after transport
+ *      (SimulatorUtilities.hpp).  All use the resident half-face fluxes and operate on the own cells. ----
+ * eu_cell_velocity: estimateCellVelocity (:59-86): v_c = (1/volume) sum_f flux_f (face centroid - cell centroid);
+ *                   out 3 doubles per own cell.
+ * eu_phase_velocities: computePhaseVelocities (:153-170) from a cell velocity field and saturations
+ *                   (scalar mobility: v_w = f_w v, v_o = v - v_w; diagonal tensor mobility: v_w = F v with
+ *                   F = lambda_w (lambda_w + lambda_o)^-1); out 3 doubles per own cell and phase.
+ * eu_fractional_flow: rp.fractionalFlow(c, S[c]) per own cell (writeVtkOutput loop, :276-279). */
+int eu_cell_velocity(eu_handle h, double* cell_velocity);
+int eu_phase_velocities(eu_handle h, const double* saturation, const double* cell_velocity,
+                        double* water_velocity, double* oil_velocity);
+int eu_fractional_flow(eu_handle h, const double* saturation, double* frac_flow);
+
 /* ---- multi-GPU plumbing (one process per GPU; see DESIGN.md "Multi-GPU") ----------------
  * Each rank owns a contiguous range of global cells (z-slab) and holds the remote cells its faces touch
  * as ghost cells.  After every substep the new saturations (and, in FAST mode, capillary pressures) of

@@ -107,6 +107,7 @@ struct eu_solver {
     int contracted_mg = -1;
     // ---- state
     DevBuf<double> d_S[2], d_pc[2], d_S_init, d_hf_flux, d_residual, d_block_min, d_scalars;
+    DevBuf<double> d_diag;             // scratch of the diagnostics (eu_diag.cu), allocated on first use
     DevBuf<unsigned long long> d_fail_key;
     DevBuf<int> d_src_cell;
     DevBuf<double> d_src_rate;
@@ -1110,6 +1111,150 @@ int eu_small_step(eu_handle h, double dt, const double gravity[3], int n_src, co
         if (bad_value) *bad_value = v;
         return EU_ERR_SAT_RANGE;
     }
+    return EU_OK;
+}
+
+// EulerUpstreamResidual::computeResidual as an operator (Residual_impl.hpp:472-505).  Runs the substep kernel of
+// the current mode with dt = 0 and the range check off on a scratch copy of the state: the residual it writes is
+// exactly what smallTimeStep would have used; the resident saturation and the solver parameters are untouched.
+int eu_compute_residual(eu_handle h, const double* saturation, const double gravity[3], const double* hf_flux,
+                        int n_src, const int* src_cell, const double* src_rate,
+                        int method_viscous, int method_gravity, int method_capillary, double* sat_delta)
+{
+    if (!h || !saturation || !gravity || !sat_delta) return EU_ERR_ARG;
+    if (!h->grid_ready) return fail(h, EU_ERR_ARG, "grid not ready");
+    if (!hf_flux && !h->state_ready) return fail(h, EU_ERR_ARG, "no resident fluxes: pass hf_flux or call eu_upload_state first");
+    if (h->cfg.world_size > 1) return fail(h, EU_ERR_UNSUPPORTED, "eu_compute_residual is a single-rank entry point");
+    EU_CUDA(h, cudaSetDevice(h->cfg.device));
+    const size_t nbytes = size_t(h->n_local)*sizeof(double);
+    const int in = h->cur ^ 1;                   // the buffer that does not hold the resident state
+    // The resident state is parked in d_S_init while both ping-pong buffers serve as scratch.
+    EU_CUDA(h, cudaMemcpyAsync(h->d_S_init.p, h->d_S[h->cur].p, nbytes, cudaMemcpyDeviceToDevice, h->st));
+    EU_CUDA(h, cudaMemcpyAsync(h->d_S[in].p, saturation, nbytes, cudaMemcpyHostToDevice, h->st));
+    if (hf_flux) {
+        EU_CUDA(h, cudaMemcpyAsync(h->d_hf_flux.p, hf_flux, size_t(h->H)*sizeof(double), cudaMemcpyHostToDevice, h->st));
+        h->state_ready = true;
+    }
+    int rc, nls = 0, zero = 0, launches = 0;
+    if ((rc = upload_sources(h, n_src, src_cell, src_rate, &nls))) return rc;
+    const eu_params saved = h->par;
+    h->par.method_viscous = method_viscous != 0;
+    h->par.method_gravity = method_gravity != 0;
+    h->par.method_capillary = method_capillary != 0;
+    h->par.check_sat = 0;
+    h->par.clamp_sat = 0;
+    double cfl[3];
+    rc = compute_cfl(h, gravity, false, false, false, cfl, &zero, &launches);     // compacts the fluxes (FAST)
+    if (!rc) rc = ensure_contracted(h, gravity);
+    if (!rc) {
+        const unsigned long long none = ~0ULL;
+        cudaMemcpyAsync(h->d_fail_key.p, &none, sizeof(none), cudaMemcpyHostToDevice, h->st);
+        h->cur = in;
+        if (h->mode == EU_MODE_FAST)
+            eu_launch_fast_state(h->grid(), h->tab, h->fast(), h->d_S[in].p, method_capillary ? h->d_pc[in].p : nullptr,
+                                 h->d_lam[in].p, 0, h->n_local, h->st);
+        EuStepArgs a = step_args(h, 0.0, gravity, nls, 0);
+        a.residual_out = h->d_residual.p;
+        if (launch_substep(h, a, false) < 0) rc = EU_ERR_CUDA;
+        h->cur = in ^ 1;
+    }
+    h->par = saved;
+    if (rc) return rc;
+    EU_CUDA(h, cudaMemcpyAsync(sat_delta, h->d_residual.p + h->own_lo, size_t(h->own_hi - h->own_lo)*sizeof(double),
+                               cudaMemcpyDeviceToHost, h->st));
+    EU_CUDA(h, cudaMemcpyAsync(h->d_S[h->cur].p, h->d_S_init.p, nbytes, cudaMemcpyDeviceToDevice, h->st));
+    EU_CUDA(h, cudaStreamSynchronize(h->st));
+    EU_CUDA(h, cudaGetLastError());
+    return EU_OK;
+}
+
+// EulerUpstreamResidual::computeCapPressures (Residual_impl.hpp:459-467) / computeCapPressure
+// (SimulatorUtilities.hpp:219-230): the bit-exact kernel in every mode.
+int eu_compute_cap_pressures(eu_handle h, const double* saturation, double* cap_pressures)
+{
+    if (!h || !saturation || !cap_pressures) return EU_ERR_ARG;
+    if (!h->grid_ready) return fail(h, EU_ERR_ARG, "grid not ready");
+    EU_CUDA(h, cudaSetDevice(h->cfg.device));
+    const size_t nbytes = size_t(h->n_local)*sizeof(double);
+    const int scratch = h->cur ^ 1;
+    EU_CUDA(h, cudaMemcpyAsync(h->d_S[scratch].p, saturation, nbytes, cudaMemcpyHostToDevice, h->st));
+    eu_launch_strict_pc(h->grid(), h->tab, h->d_S[scratch].p, h->d_residual.p, h->st);
+    EU_CUDA(h, cudaMemcpyAsync(cap_pressures, h->d_residual.p, nbytes, cudaMemcpyDeviceToHost, h->st));
+    EU_CUDA(h, cudaStreamSynchronize(h->st));
+    EU_CUDA(h, cudaGetLastError());
+    return EU_OK;
+}
+
+// ---- diagnostics (eu_diag.cu) ------------------------------------------------------------------------------
+namespace {
+// scratch for the diagnostics: 3 doubles per own cell and field, allocated on first use
+int diag_scratch(eu_handle h, int fields)
+{
+    const size_t need = size_t(fields)*3*size_t(std::max(1, h->own_hi - h->own_lo));
+    if (h->d_diag.n < need) EU_CUDA(h, h->d_diag.alloc(need));
+    return EU_OK;
+}
+}
+
+int eu_cell_velocity(eu_handle h, double* cell_velocity)
+{
+    if (!h || !cell_velocity) return EU_ERR_ARG;
+    if (!h->state_ready) return fail(h, EU_ERR_ARG, "no resident fluxes (eu_upload_state)");
+    EU_CUDA(h, cudaSetDevice(h->cfg.device));
+    int rc;
+    if ((rc = diag_scratch(h, 3))) return rc;
+    const size_t n3 = 3*size_t(h->own_hi - h->own_lo);
+    eu_launch_cell_velocity(h->grid(), h->d_hf_flux.p, h->d_diag.p, h->st);
+    EU_CUDA(h, cudaMemcpyAsync(cell_velocity, h->d_diag.p, n3*sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    EU_CUDA(h, cudaStreamSynchronize(h->st));
+    EU_CUDA(h, cudaGetLastError());
+    return EU_OK;
+}
+
+int eu_phase_velocities(eu_handle h, const double* saturation, const double* cell_velocity,
+                        double* water_velocity, double* oil_velocity)
+{
+    if (!h || !water_velocity || !oil_velocity) return EU_ERR_ARG;
+    if (!h->grid_ready) return fail(h, EU_ERR_ARG, "grid not ready");
+    if (!saturation && !h->state_ready) return fail(h, EU_ERR_ARG, "no resident state (eu_upload_state)");
+    if (!cell_velocity && !h->state_ready) return fail(h, EU_ERR_ARG, "no resident fluxes (eu_upload_state)");
+    EU_CUDA(h, cudaSetDevice(h->cfg.device));
+    int rc;
+    if ((rc = diag_scratch(h, 3))) return rc;
+    const size_t n3 = 3*size_t(h->own_hi - h->own_lo);
+    double* cv = h->d_diag.p;
+    double* vw = cv + n3;
+    double* vo = vw + n3;
+    const double* S = h->d_S[h->cur].p;                   // NULL saturation: the resident state
+    if (saturation) {
+        EU_CUDA(h, cudaMemcpyAsync(h->d_S[h->cur ^ 1].p, saturation, size_t(h->n_local)*sizeof(double), cudaMemcpyHostToDevice, h->st));
+        S = h->d_S[h->cur ^ 1].p;
+    }
+    if (cell_velocity) EU_CUDA(h, cudaMemcpyAsync(cv, cell_velocity, n3*sizeof(double), cudaMemcpyHostToDevice, h->st));
+    else eu_launch_cell_velocity(h->grid(), h->d_hf_flux.p, cv, h->st);       // NULL: from the resident fluxes
+    eu_launch_phase_velocities(h->grid(), h->tab, S, cv, vw, vo, h->st);
+    EU_CUDA(h, cudaMemcpyAsync(water_velocity, vw, n3*sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    EU_CUDA(h, cudaMemcpyAsync(oil_velocity, vo, n3*sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    EU_CUDA(h, cudaStreamSynchronize(h->st));
+    EU_CUDA(h, cudaGetLastError());
+    return EU_OK;
+}
+
+int eu_fractional_flow(eu_handle h, const double* saturation, double* frac_flow)
+{
+    if (!h || !frac_flow) return EU_ERR_ARG;
+    if (!h->grid_ready) return fail(h, EU_ERR_ARG, "grid not ready");
+    if (!saturation && !h->state_ready) return fail(h, EU_ERR_ARG, "no resident state (eu_upload_state)");
+    EU_CUDA(h, cudaSetDevice(h->cfg.device));
+    const double* S = h->d_S[h->cur].p;
+    if (saturation) {
+        EU_CUDA(h, cudaMemcpyAsync(h->d_S[h->cur ^ 1].p, saturation, size_t(h->n_local)*sizeof(double), cudaMemcpyHostToDevice, h->st));
+        S = h->d_S[h->cur ^ 1].p;
+    }
+    eu_launch_fractional_flow(h->grid(), h->tab, S, h->d_residual.p, h->st);
+    EU_CUDA(h, cudaMemcpyAsync(frac_flow, h->d_residual.p, size_t(h->own_hi - h->own_lo)*sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    EU_CUDA(h, cudaStreamSynchronize(h->st));
+    EU_CUDA(h, cudaGetLastError());
     return EU_OK;
 }
 

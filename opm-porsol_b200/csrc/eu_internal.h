@@ -198,6 +198,11 @@ void eu_launch_halo_push(const int* send_src, const int* send_dst, int n, const 
                          unsigned epoch, cudaStream_t st);
 void eu_launch_halo_wait(const unsigned* my_flags, const int* wait_ranks, int n_wait, unsigned epoch,
                          long long timeout_cycles, int* err_flag, cudaStream_t st);
+// ---- eu_diag.cu (-fmad=false): diagnostics on resident data (common/SimulatorUtilities.hpp) -------------
+void eu_launch_cell_velocity(const EuGridDev& g, const double* hf_flux, double* out, cudaStream_t st);
+void eu_launch_fractional_flow(const EuGridDev& g, const EuTablesDev& t, const double* S, double* out, cudaStream_t st);
+void eu_launch_phase_velocities(const EuGridDev& g, const EuTablesDev& t, const double* S, const double* cell_v,
+                                double* vw, double* vo, cudaStream_t st);
 // ---- eu_fast.cu ------------------------------------------------------------------------------
 void eu_launch_fast_state(const EuGridDev& g, const EuTablesDev& t, const EuFastDev& f, const double* S, double* pc,
                           double2* lam, int lo, int hi, cudaStream_t st);
