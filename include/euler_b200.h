@@ -205,7 +205,8 @@ int eu_small_step(eu_handle h, double dt, const double gravity[3],
  * saturation: all local cells (host); hf_flux: all local half-faces (host), or NULL to reuse the fluxes already
  * resident from eu_upload_state / the last eu_transport_solve; sat_delta: the own cells (host, out).
  * The method flags are arguments, as in the reference; the solver's eu_params are not consulted or changed,
- * nor is the resident saturation. */
+ * nor is the resident saturation.  With method_capillary set the call includes computeCapPressures(saturation)
+ * (:459-467), which the reference's callers issue separately beforehand (EulerUpstream_impl.hpp:362-369). */
 int eu_compute_residual(eu_handle h, const double* saturation, const double gravity[3], const double* hf_flux,
                         int n_src, const int* src_cell, const double* src_rate,
                         int method_viscous, int method_gravity, int method_capillary, double* sat_delta);
@@ -217,10 +218,13 @@ int eu_compute_cap_pressures(eu_handle h, const double* saturation, double* cap_
  *      (SimulatorUtilities.hpp).  All use the resident half-face fluxes and operate on the own cells. ----
  * eu_cell_velocity: estimateCellVelocity (:59-86): v_c = (1/volume) sum_f flux_f (face centroid - cell centroid);
  *                   out 3 doubles per own cell.
- * eu_phase_velocities: computePhaseVelocities (:153-170) from a cell velocity field and saturations
- *                   (scalar mobility: v_w = f_w v, v_o = v - v_w; diagonal tensor mobility: v_w = F v with
- *                   F = lambda_w (lambda_w + lambda_o)^-1); out 3 doubles per own cell and phase.
- * eu_fractional_flow: rp.fractionalFlow(c, S[c]) per own cell (writeVtkOutput loop, :276-279). */
+ * eu_phase_velocities: computePhaseVelocities (:153-170): v_w = v f, v_o = v (1.0 - f) with f = rp.fractionalFlow(c, S[c]);
+ *                   saturation NULL = the resident state (else all local cells, host), cell_velocity NULL = computed
+ *                   from the resident fluxes (else 3 doubles per own cell, host); out 3 doubles per own cell and phase.
+ * eu_fractional_flow: rp.fractionalFlow(c, S[c]) per own cell (writeVtkOutput loop, :273-279;
+ *                   ReservoirPropertyCapillary_impl.hpp:83-88, ...AnisotropicRelperm_impl.hpp:57-72); saturation NULL =
+ *                   the resident state.
+ * All three follow the reference's operation order (bit-identical results in every arithmetic mode). */
 int eu_cell_velocity(eu_handle h, double* cell_velocity);
 int eu_phase_velocities(eu_handle h, const double* saturation, const double* cell_velocity,
                         double* water_velocity, double* oil_velocity);

@@ -102,6 +102,7 @@ struct eu_solver {
     long long F = 0;
     int n_slices = 0;
     bool use_nn = false;
+    int prefetch = 1;                  // EU_PREFETCH=0 turns the L2 prefetch of the marches off (tuning knob)
     bool contracted = false;
     double contracted_gravity[3] = { 0, 0, 0 };
     int contracted_mg = -1;
@@ -167,6 +168,7 @@ struct eu_solver {
         f.classes = d_classes.p; f.n_classes = n_classes; f.slice_base = d_slice_base.p; f.rec = d_rec.p; f.desc = d_desc.p;
         f.qg = d_qg.p; f.T = d_T.p; f.nn = use_nn ? d_nn.p : nullptr;
         f.inv_porevol = d_inv_porevol.p; f.pcscale = d_pcscale.p; f.rock8 = d_rock8.p; f.F = F;
+        f.prefetch = prefetch;
         return f;
     }
     int global_to_local(int gcell) const
@@ -348,7 +350,8 @@ int build_items(eu_handle h, int lo, int hi)
     const bool use_classes = !(env_noclass && atoi(env_noclass) != 0) && (h->cfg.world_size <= 1 || fused_halo(h));
     for (int s = lo; s < hi && use_classes; ++s) {
         if (s*EU_SLICE < h->own_lo || (s + 1)*EU_SLICE > h->own_hi) continue;
-        if (base[size_t(s) + 1] - base[size_t(s)] != 6*EU_SLICE) continue;
+        const int width = (base[size_t(s) + 1] - base[size_t(s)])/EU_SLICE;
+        if (width < 6 || width > 30) continue;
         const int2* d = &desc[size_t(base[size_t(s)]/EU_SLICE)];
         // regular slots in (-d, +d) pairs
         int mag[3] = { 0, 0, 0 }, neg[3] = { -1, -1, -1 }, pos[3] = { -1, -1, -1 }, npairs = 0;
@@ -399,6 +402,7 @@ int build_items(eu_handle h, int lo, int hi)
             key.v[3*q] = c.nb_off[q]; key.v[3*q + 1] = c.fid_mul[q]; key.v[3*q + 2] = c.fid_off[q];
         }
         for (int j = 0; j < 6; ++j) if (d[j].y == -1) c.rec_mask |= 1 << j;
+        for (int j = 6; j < width; ++j) if (d[j].y != -2) c.rec_mask |= 1 << j;      // extra slots: always from the records
         c.D = (march >= 0 && pos[march] >= 0) ? mag[march] : 0;
         key.v[18] = c.rec_mask; key.v[19] = c.D;
         auto it = class_of_key.find(key);
@@ -652,6 +656,7 @@ int eu_create(const eu_config* cfg, eu_handle* out)
     eu_default_params(&h->par);
     h->mode = EU_MODE_STRICT;
     h->n_sms = prop.multiProcessorCount;
+    { const char* e = getenv("EU_PREFETCH"); if (e) h->prefetch = atoi(e) != 0; }
     std::memset(&h->fluid, 0, sizeof(h->fluid));
     std::memset(&h->tab, 0, sizeof(h->tab));
     if ((e = cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking)) != cudaSuccess ||
@@ -952,10 +957,11 @@ int eu_grid_end(eu_handle h)
         EU_CUDA(h, cudaMemsetAsync(h->d_fid_of_hf.p, 0xff, H*sizeof(int), h->st));
     } else {
         h->n_slices = (h->n_local + EU_SLICE - 1)/EU_SLICE;
-        DevBuf<int> d_width, d_nown;
+        DevBuf<int> d_width;
+        DevBuf<unsigned char> d_slot;          // canonical slot of every half-face (setup only)
         EU_CUDA(h, d_width.alloc(size_t(h->n_slices)));
-        EU_CUDA(h, d_nown.alloc(size_t(h->n_slices)));
-        eu_launch_slice_count(g, h->d_owner_hf.p, d_width.p, d_nown.p, h->st);
+        EU_CUDA(h, d_slot.alloc(std::max<size_t>(H, 1)));
+        eu_launch_canonical_slots(g, d_slot.p, d_width.p, h->st);
         std::vector<int> width(size_t(h->n_slices));
         EU_CUDA(h, cudaMemcpyAsync(width.data(), d_width.p, width.size()*sizeof(int), cudaMemcpyDeviceToHost, h->st));
         EU_CUDA(h, cudaStreamSynchronize(h->st));
@@ -976,8 +982,8 @@ int eu_grid_end(eu_handle h)
         EU_CUDA(h, h->d_rec.alloc(size_t(rec_total)));
         EU_CUDA(h, h->d_desc.alloc(size_t(rec_total/EU_SLICE) + 1));
         EU_CUDA(h, cudaMemsetAsync(h->d_flags.p, 0, 4*sizeof(int), h->st));
-        eu_launch_assign_fid(g, h->d_owner_hf.p, h->d_fid_of_hf.p, h->st);
-        eu_launch_build_records(g, h->d_owner_hf.p, h->d_fid_of_hf.p, h->d_slice_base.p, h->d_rec.p, h->d_desc.p,
+        eu_launch_assign_fid(g, h->d_owner_hf.p, d_slot.p, h->d_fid_of_hf.p, h->st);
+        eu_launch_build_records(g, h->d_owner_hf.p, h->d_fid_of_hf.p, d_slot.p, h->d_slice_base.p, h->d_rec.p, h->d_desc.p,
                                 h->d_flags.p + 1, h->st);
         int nreg[4] = { 0, 0, 0, 0 };
         EU_CUDA(h, cudaMemcpyAsync(nreg, h->d_flags.p, sizeof(nreg), cudaMemcpyDeviceToHost, h->st));

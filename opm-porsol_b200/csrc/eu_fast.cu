@@ -369,6 +369,11 @@ __device__ __forceinline__ double ldg_f64(const double* p)
     return v;
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p)
+{
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+}
+
 // state carried along a march
 struct MarchCarry {
     double S0, lw0, lo0, pc0, dS4;     // this cell; dS4 = flux of its slot-4 face in the lo cell's frame
@@ -411,7 +416,8 @@ __device__ __forceinline__ void march_head(const TabLayout& L, const EuTablesDev
 // one cell of a march; advances the carry to the cell across slot 5
 template <bool ROCKS, bool MULTIROCK, bool CAP, bool NN, bool RECORDS>
 __device__ __forceinline__ void march_step(const TabLayout& L, const EuGridDev& g, const EuTablesDev& t, const EuFastDev& f,
-                                           const EuStepArgs& a, const EuSliceClass* __restrict__ cl, int c, int lane, MarchCarry& m)
+                                           const EuStepArgs& a, const EuSliceClass* __restrict__ cl, int c, int lane, bool more,
+                                           MarchCarry& m)
 {
     constexpr int kOrder[5] = { 5, 3, 2, 1, 0 };       // far neighbours first: their lines take longest to arrive
     int nb[6], fid[6];
@@ -426,6 +432,28 @@ __device__ __forceinline__ void march_step(const TabLayout& L, const EuGridDev& 
     }
     const double S5 = ldg_f64(a.S_in + nb[5]);
     const double inv_pv = ldg_f64(f.inv_porevol + c);
+    if (f.prefetch && more) {
+        // the lines the next cell of the march (c + D) will load, requested into L2 now: its z+ and y neighbours'
+        // mobility pairs (the x neighbours share the lines of lam[c + D], loaded above as slot 5), the {q, G} pairs of
+        // its faces, its z+ neighbour's saturation and its 1/porevol.  No registers are tied up by these requests.
+        const int D = cl->D;
+        prefetch_l2(a.lam_in + nb[5] + D);
+        prefetch_l2(a.lam_in + nb[3] + D);
+        prefetch_l2(a.lam_in + nb[2] + D);
+        prefetch_l2(f.qg + fid[5] + D*cl->fid_mul[5]);
+        prefetch_l2(f.qg + fid[3] + D*cl->fid_mul[3]);
+        prefetch_l2(f.qg + fid[2] + D*cl->fid_mul[2]);
+        prefetch_l2(f.qg + fid[1] + D*cl->fid_mul[1]);
+        prefetch_l2(a.S_in + nb[5] + D);
+        prefetch_l2(f.inv_porevol + c + D);
+        if (CAP) {
+            prefetch_l2(a.pc_in + nb[5] + D);
+            prefetch_l2(f.T + fid[5] + D*cl->fid_mul[5]);
+            prefetch_l2(f.T + fid[3] + D*cl->fid_mul[3]);
+            prefetch_l2(f.T + fid[1] + D*cl->fid_mul[1]);
+            prefetch_l2(f.pcscale + c + D);
+        }
+    }
     double S1[6], T[6], pc1[6], nn[6];
     int rk[6];
 #pragma unroll
@@ -453,8 +481,8 @@ __device__ __forceinline__ void march_step(const TabLayout& L, const EuGridDev& 
     }
     if (RECORDS) {                      // boundary / fault faces of this class, from the SELL records
         const int base = f.slice_base[c >> 5];
-        acc += gather_cell_loop<ROCKS, MULTIROCK, CAP, NN>(L, g, t, f, a, f.rec + base + lane, 6, (unsigned)cl->rec_mask, c, m.S0,
-                                                           m.rock0, m.pc0, m.lw0, m.lo0);
+        acc += gather_cell_loop<ROCKS, MULTIROCK, CAP, NN>(L, g, t, f, a, f.rec + base + lane, 32 - __clz(cl->rec_mask),
+                                                           (unsigned)cl->rec_mask, c, m.S0, m.rock0, m.pc0, m.lw0, m.lo0);
     }
     double pcn;
     finish_cell<ROCKS, MULTIROCK, CAP>(L, t, f, a, c, m.S0, m.rock0, m.lw0, m.lo0, inv_pv, acc, pcn);
@@ -472,7 +500,7 @@ __device__ __forceinline__ void march_item_impl(const TabLayout& L, const EuGrid
     MarchCarry m;
     march_head<ROCKS, MULTIROCK, CAP, NN>(L, t, f, a, cl, c, m);
     for (int i = 0; i < len; ++i) {
-        march_step<ROCKS, MULTIROCK, CAP, NN, RECORDS>(L, g, t, f, a, cl, c, lane, m);
+        march_step<ROCKS, MULTIROCK, CAP, NN, RECORDS>(L, g, t, f, a, cl, c, lane, i + 1 < len, m);
         c += D;
     }
 }
@@ -669,7 +697,10 @@ static void launch_variant(const EuGridDev& g, const EuTablesDev& t, const EuFas
     kern<<<blocks, kBlock, smem, st>>>(g, t, f, a, halo, slice_lo, slice_hi, (int)smem_tables);
 }
 
-// EU_FAST_VARIANT (tuning knob, read once): resident blocks per SM the kernel is compiled for
+// EU_FAST_VARIANT (tuning knob, read once): resident blocks per SM the kernel is compiled for.
+//   0 (default)  by variant: 2 blocks (128 registers) with the capillary term -- at 80 registers that variant spills
+//                128-1400 bytes per thread (-Xptxas -v) --, 3 blocks (80 registers) without
+//   1 / 2 / 3    force 2 / 4 / 3 blocks per SM
 static int fast_variant()
 {
     static int v = -1;
@@ -681,7 +712,9 @@ template <bool ROCKS, bool MULTIROCK, bool CAP, bool NN>
 static void launch_fast(const EuGridDev& g, const EuTablesDev& t, const EuFastDev& f, const EuStepArgs& a,
                         const EuHaloDev& halo, int slice_lo, int slice_hi, int n_sms, size_t smem, cudaStream_t st)
 {
-    switch (fast_variant()) {
+    int v = fast_variant();
+    if (v == 0) v = CAP ? 1 : 3;
+    switch (v) {
     case 1:  launch_variant<ROCKS, MULTIROCK, CAP, NN, 3, 4, 2>(g, t, f, a, halo, slice_lo, slice_hi, n_sms, smem, st); break;
     case 2:  launch_variant<ROCKS, MULTIROCK, CAP, NN, 3, 4, 4>(g, t, f, a, halo, slice_lo, slice_hi, n_sms, smem, st); break;
     default: launch_variant<ROCKS, MULTIROCK, CAP, NN, 3, 4, 3>(g, t, f, a, halo, slice_lo, slice_hi, n_sms, smem, st); break;

@@ -91,7 +91,8 @@ struct EuStrictDev {
 // as face 4 of the next (the same face, evaluated once), together with the neighbour's saturation and mobilities.
 // Slots that are not regular in this class (boundary faces, fault faces) are explicit: the regular code runs on a
 // dummy face with zero flux for them (face id F, one past the real faces) and the real face is added from the slice's
-// SELL records afterwards.
+// SELL records afterwards.  Slices wider than six slots (cells with split faces next to a fault plane) belong to a
+// class as well: their slots 6.. are explicit.
 #define EU_MAX_CLASSES 40
 #define EU_ITEM_GENERIC 0xffff
 struct EuSliceClass {
@@ -99,7 +100,7 @@ struct EuSliceClass {
     int fid_mul[6];           // regular slot: face = cell*1 + fid_off;    explicit: cell*0 + (the all-zero face F)
     int fid_off[6];
     int D;                    // march stride in cells (multiple of 32); 0 = items of this class have length 1
-    int rec_mask;             // bit j: slot j of the SELL records is an explicit face of this class
+    int rec_mask;             // bit j: slot j of the SELL records is an explicit face of this class (j < 31)
     int pad[2];
 };
 
@@ -122,6 +123,7 @@ struct EuFastDev {
     const double* pcscale;
     const unsigned char* rock8;
     long long F;
+    int prefetch;             // marches request the next cell's lines into L2 one step ahead
 };
 
 struct EuStepArgs {
@@ -173,10 +175,10 @@ void eu_launch_translate_nbr(int* hf_nbr, long long H, const int* range_first, c
 void eu_launch_owner(const EuGridDev& g, int* owner_hf, int* err_flag, cudaStream_t st);
 void eu_launch_strict_list(const EuGridDev& g, const int* owner_hf, int2* list, cudaStream_t st);
 void eu_launch_porevol(const EuGridDev& g, double* porevol, cudaStream_t st);
-void eu_launch_slice_count(const EuGridDev& g, const int* owner_hf, int* slice_width, int* slice_nown, cudaStream_t st);
-void eu_launch_assign_fid(const EuGridDev& g, const int* owner_hf, int* fid_of_hf, cudaStream_t st);
-void eu_launch_build_records(const EuGridDev& g, const int* owner_hf, const int* fid_of_hf, const int* slice_base,
-                             int2* rec, int2* desc, int* n_regular_slots, cudaStream_t st);
+void eu_launch_canonical_slots(const EuGridDev& g, unsigned char* slot_of_hf, int* slice_width, cudaStream_t st);
+void eu_launch_assign_fid(const EuGridDev& g, const int* owner_hf, const unsigned char* slot_of_hf, int* fid_of_hf, cudaStream_t st);
+void eu_launch_build_records(const EuGridDev& g, const int* owner_hf, const int* fid_of_hf, const unsigned char* slot_of_hf,
+                             const int* slice_base, int2* rec, int2* desc, int* n_regular_slots, cudaStream_t st);
 void eu_launch_contract(const EuGridDev& g, const EuTablesDev& t, const int* owner_hf, const int* fid_of_hf,
                         const double gravity[3], int method_gravity, double* G, double* T, double* nn,
                         double* nn_maxdev, cudaStream_t st);

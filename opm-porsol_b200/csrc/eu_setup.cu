@@ -2,6 +2,8 @@
 // Compile with -fmad=false: everything numeric here follows the reference's operation order
 // (see eu_strict_math.cuh) and is bit-identical to it.
 #include "eu_internal.h"
+
+#include <climits>
 #include "eu_strict_math.cuh"
 
 namespace {
@@ -127,40 +129,117 @@ __global__ void k_porevol(EuGridDev g, double* __restrict__ porevol)
 // ---------------------------------------------------------------------------------------
 // SELL-32 structure for the FAST kernel
 // ---------------------------------------------------------------------------------------
-__global__ void k_slice_count(EuGridDev g, const int* __restrict__ owner_hf, int* __restrict__ slice_width,
-                              int* __restrict__ slice_nown)
+// Canonical face slots of the FAST layout.  The SELL slot of a half-face (and with it the plane of its face id) need
+// not be the cell's local face index: FAST results are gated by a tolerance, not by the reference's summation order
+// (STRICT keeps that order through its own list).  Per slice of 32 cells the neighbour offsets d = nbr - cell that a
+// majority of the cells share become the slice's standard slots, in ascending order of d; a cell's remaining faces
+// (boundary faces, fault faces, split faces) take its empty standard slots first and then extra slots.  A Cartesian
+// slice is unchanged up to a permutation; a slice next to a fault plane keeps five regular slots instead of losing
+// every slot behind the first cell with an extra face.  One warp per slice; cells with more than kMaxCanon faces
+// keep their local order.
+constexpr int kMaxCanon = 16;
+constexpr int kNoOffset = INT_MIN;
+
+__global__ void k_canonical_slots(EuGridDev g, unsigned char* __restrict__ slot_of_hf, int* __restrict__ slice_width)
 {
     const int warp = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     const int n_slices = (g.n_local + EU_SLICE - 1)/EU_SLICE;
     if (warp >= n_slices) return;
     const int c = warp*EU_SLICE + lane;
-    int cnt = 0, nown = 0;
-    if (c < g.n_local) {
-        const int b = g.hf_offset[c];
-        cnt = g.hf_offset[c + 1] - b;
-        for (int k = 0; k < cnt; ++k) nown += (owner_hf[b + k] == b + k);
+    int b = 0, cnt = 0;
+    if (c < g.n_local) { b = g.hf_offset[c]; cnt = g.hf_offset[c + 1] - b; }
+    int maxcnt = cnt;
+    for (int o = 16; o > 0; o >>= 1) maxcnt = max(maxcnt, __shfl_xor_sync(0xffffffffu, maxcnt, o));
+    int width = 0;
+    if (maxcnt > kMaxCanon) {                       // warp-uniform: identity
+        for (int j = 0; j < cnt; ++j) slot_of_hf[b + j] = (unsigned char)min(j, 255);
+        width = maxcnt;
+    } else {
+        int d[kMaxCanon];
+#pragma unroll
+        for (int j = 0; j < kMaxCanon; ++j) {
+            d[j] = kNoOffset;
+            if (j < cnt) {
+                const int n = g.hf_nbr[b + j];
+                int other = n;
+                if (n < 0) {
+                    const int bi = -2 - n;
+                    other = (g.bnd_kind[bi] == EU_HF_PERIODIC) ? g.bnd_partner_cell[bi] : -1;
+                }
+                if (other >= 0 && other != c) d[j] = other - c;
+            }
+        }
+        // standard offsets by majority vote; every face of every lane is a candidate once
+        const unsigned active = __ballot_sync(0xffffffffu, cnt > 0);
+        const int n_active = __popc(active);
+        int stdo[8];
+        int n_std = 0;
+        for (int l = 0; l < 32; ++l) {
+#pragma unroll
+            for (int j = 0; j < kMaxCanon; ++j) {
+                if (j >= maxcnt) break;
+                const int cand = __shfl_sync(0xffffffffu, d[j], l);
+                if (cand == kNoOffset) continue;
+                bool known = false;
+                for (int q = 0; q < n_std; ++q) known = known || stdo[q] == cand;
+                if (known || n_std >= 8) continue;
+                bool mine = false;
+#pragma unroll
+                for (int i = 0; i < kMaxCanon; ++i) mine = mine || d[i] == cand;
+                const int votes = __popc(__ballot_sync(0xffffffffu, mine));
+                if (2*votes > n_active) stdo[n_std++] = cand;
+            }
+        }
+        for (int i = 1; i < n_std; ++i) {           // ascending (warp-uniform insertion sort)
+            const int v = stdo[i];
+            int q = i;
+            while (q > 0 && stdo[q - 1] > v) { stdo[q] = stdo[q - 1]; --q; }
+            stdo[q] = v;
+        }
+        // standard faces to their slots (the first face of a cell with that offset), the others to the free slots
+        unsigned used = 0u;
+        int slot[kMaxCanon];
+#pragma unroll
+        for (int j = 0; j < kMaxCanon; ++j) {
+            slot[j] = -1;
+            if (j < cnt && d[j] != kNoOffset) {
+                for (int q = 0; q < n_std; ++q) {
+                    if (stdo[q] == d[j] && !((used >> q) & 1u)) { slot[j] = q; used |= 1u << q; break; }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kMaxCanon; ++j) {
+            if (j < cnt) {
+                if (slot[j] < 0) {
+                    const int q = __ffs(~used) - 1;
+                    slot[j] = q;
+                    used |= 1u << q;
+                }
+                slot_of_hf[b + j] = (unsigned char)slot[j];
+                width = max(width, slot[j] + 1);
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) width = max(width, __shfl_xor_sync(0xffffffffu, width, o));
     }
-    for (int o = 16; o > 0; o >>= 1) {
-        cnt = max(cnt, __shfl_xor_sync(0xffffffffu, cnt, o));
-        nown += __shfl_xor_sync(0xffffffffu, nown, o);
-    }
-    if (lane == 0) { slice_width[warp] = cnt; slice_nown[warp] = nown; }
+    if (lane == 0) slice_width[warp] = width;
 }
 
-// face id of an own half-face = slot*n_local + cell ("plane" = local face slot of the owner): coalesced per
+// face id of an own half-face = slot*n_local + cell ("plane" = canonical slot of the owner's half-face): coalesced per
 // plane, and for a regular neighbour pattern the id of the neighbour's twin face is affine in the cell index
-__global__ void k_assign_fid(EuGridDev g, const int* __restrict__ owner_hf, int* __restrict__ fid_of_hf)
+__global__ void k_assign_fid(EuGridDev g, const int* __restrict__ owner_hf, const unsigned char* __restrict__ slot_of_hf,
+                             int* __restrict__ fid_of_hf)
 {
     int c = blockIdx.x*blockDim.x + threadIdx.x;
     if (c >= g.n_local) return;
     const int b = g.hf_offset[c], e = g.hf_offset[c + 1];
-    for (int h = b; h < e; ++h) fid_of_hf[h] = (owner_hf[h] == h) ? (h - b)*g.n_local + c : -1;
+    for (int h = b; h < e; ++h) fid_of_hf[h] = (owner_hf[h] == h) ? int(slot_of_hf[h])*g.n_local + c : -1;
 }
 
 __global__ void k_build_records(EuGridDev g, const int* __restrict__ owner_hf, const int* __restrict__ fid_of_hf,
-                                const int* __restrict__ slice_base, int2* __restrict__ rec, int2* __restrict__ desc,
-                                int* __restrict__ n_regular_slots)
+                                const unsigned char* __restrict__ slot_of_hf, const int* __restrict__ slice_base,
+                                int2* __restrict__ rec, int2* __restrict__ desc, int* __restrict__ n_regular_slots)
 {
     const int warp = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -171,23 +250,27 @@ __global__ void k_build_records(EuGridDev g, const int* __restrict__ owner_hf, c
     if (c < g.n_local) { b = g.hf_offset[c]; cnt = g.hf_offset[c + 1] - b; }
     const int base = slice_base[warp];
     const int width = (slice_base[warp + 1] - base)/EU_SLICE;
-    for (int j = 0; j < width; ++j) {
+    // every lane owns column `lane` of the slice: pad it, then drop its faces into their canonical slots
+    for (int j = 0; j < width; ++j) rec[(long long)base + (long long)j*EU_SLICE + lane] = make_int2(EU_REC_PAD, -1);
+    for (int k = 0; k < cnt; ++k) {
+        const int h = b + k;
+        const int o = owner_hf[h];
+        const int n = g.hf_nbr[h];
         int2 r = make_int2(EU_REC_PAD, -1);
-        if (j < cnt) {
-            const int h = b + j;
-            const int o = owner_hf[h];
-            const int n = g.hf_nbr[h];
-            if (o >= 0) {
-                r.y = fid_of_hf[o];
-                if (n >= 0) {
-                    r.x = n;
-                } else {
-                    const int bi = -2 - n;
-                    r.x = (g.bnd_kind[bi] == EU_HF_PERIODIC) ? g.bnd_partner_cell[bi] : n;
-                }
+        if (o >= 0) {
+            r.y = fid_of_hf[o];
+            if (n >= 0) {
+                r.x = n;
+            } else {
+                const int bi = -2 - n;
+                r.x = (g.bnd_kind[bi] == EU_HF_PERIODIC) ? g.bnd_partner_cell[bi] : n;
             }
         }
-        rec[(long long)base + (long long)j*EU_SLICE + lane] = r;
+        const int j = slot_of_hf[h];
+        if (j < width) rec[(long long)base + (long long)j*EU_SLICE + lane] = r;
+    }
+    for (int j = 0; j < width; ++j) {
+        const int2 r = rec[(long long)base + (long long)j*EU_SLICE + lane];      // written by this very thread
         // regular slot: every lane has an interior (or periodic) neighbour at the same offset d whose face
         // lives in the same plane k, so that nbr = c + d and fid = k*n_local + (d > 0 ? c : c + d)
         const int d = r.x - c;
@@ -658,21 +741,21 @@ void eu_launch_porevol(const EuGridDev& g, double* porevol, cudaStream_t st)
 {
     k_porevol<<<div_up(g.n_local, kThreads), kThreads, 0, st>>>(g, porevol);
 }
-void eu_launch_slice_count(const EuGridDev& g, const int* owner_hf, int* slice_width, int* slice_nown, cudaStream_t st)
+void eu_launch_canonical_slots(const EuGridDev& g, unsigned char* slot_of_hf, int* slice_width, cudaStream_t st)
 {
     const int n_slices = (g.n_local + EU_SLICE - 1)/EU_SLICE;
-    k_slice_count<<<div_up((long long)n_slices*32, kThreads), kThreads, 0, st>>>(g, owner_hf, slice_width, slice_nown);
+    k_canonical_slots<<<div_up((long long)n_slices*32, kThreads), kThreads, 0, st>>>(g, slot_of_hf, slice_width);
 }
-void eu_launch_assign_fid(const EuGridDev& g, const int* owner_hf, int* fid_of_hf, cudaStream_t st)
+void eu_launch_assign_fid(const EuGridDev& g, const int* owner_hf, const unsigned char* slot_of_hf, int* fid_of_hf, cudaStream_t st)
 {
-    k_assign_fid<<<div_up(g.n_local, kThreads), kThreads, 0, st>>>(g, owner_hf, fid_of_hf);
+    k_assign_fid<<<div_up(g.n_local, kThreads), kThreads, 0, st>>>(g, owner_hf, slot_of_hf, fid_of_hf);
 }
-void eu_launch_build_records(const EuGridDev& g, const int* owner_hf, const int* fid_of_hf, const int* slice_base,
-                             int2* rec, int2* desc, int* n_regular_slots, cudaStream_t st)
+void eu_launch_build_records(const EuGridDev& g, const int* owner_hf, const int* fid_of_hf, const unsigned char* slot_of_hf,
+                             const int* slice_base, int2* rec, int2* desc, int* n_regular_slots, cudaStream_t st)
 {
     const int n_slices = (g.n_local + EU_SLICE - 1)/EU_SLICE;
-    k_build_records<<<div_up((long long)n_slices*32, kThreads), kThreads, 0, st>>>(g, owner_hf, fid_of_hf, slice_base, rec, desc,
-                                                                                  n_regular_slots);
+    k_build_records<<<div_up((long long)n_slices*32, kThreads), kThreads, 0, st>>>(g, owner_hf, fid_of_hf, slot_of_hf, slice_base,
+                                                                                  rec, desc, n_regular_slots);
 }
 void eu_launch_contract(const EuGridDev& g, const EuTablesDev& t, const int* owner_hf, const int* fid_of_hf,
                         const double gravity[3], int method_gravity, double* G, double* T, double* nn,

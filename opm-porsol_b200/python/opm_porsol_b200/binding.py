@@ -121,6 +121,11 @@ def load_library():
     L.eu_cfl_times.argtypes = [C.c_void_p, _dp, _dp]
     L.eu_small_step.argtypes = [C.c_void_p, C.c_double, _dp, C.c_int, _ip, _dp, _dp, _ip, _dp]
     L.eu_compute_cfl_factors.argtypes = [C.POINTER(_Fluid), C.c_int, _dp, _dp, _ip, _dp]
+    L.eu_compute_residual.argtypes = [C.c_void_p, _dp, _dp, _dp, C.c_int, _ip, _dp, C.c_int, C.c_int, C.c_int, _dp]
+    L.eu_compute_cap_pressures.argtypes = [C.c_void_p, _dp, _dp]
+    L.eu_cell_velocity.argtypes = [C.c_void_p, _dp]
+    L.eu_phase_velocities.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp]
+    L.eu_fractional_flow.argtypes = [C.c_void_p, _dp, _dp]
     _LIB = L
     return L
 
@@ -384,6 +389,46 @@ class EulerUpstream:
         if rc not in (EU_OK, EU_ERR_SAT_RANGE):
             self._check(rc)
         return dict(status=rc, residual=res, bad_cell=bc.value, bad_value=bv.value)
+
+    # -- EulerUpstreamResidual::computeResidual (Residual_impl.hpp:472-505) as an operator; hf_flux=None reuses
+    #    the resident fluxes
+    def computeResidual(self, saturation, gravity, hf_flux, injection_rates, method_viscous, method_gravity, method_capillary):
+        sc, sr = self._sources(injection_rates)
+        g = np.ascontiguousarray(gravity, dtype=np.float64)
+        s = np.ascontiguousarray(saturation, dtype=np.float64)
+        fl = None if hf_flux is None else np.ascontiguousarray(hf_flux, dtype=np.float64)
+        out = np.zeros(self.L.eu_local_cells(self.h))
+        self._check(self.L.eu_compute_residual(self.h, _d(s), _d(g), None if fl is None else _d(fl), sc.shape[0], _i(sc), _d(sr),
+                                               int(bool(method_viscous)), int(bool(method_gravity)), int(bool(method_capillary)),
+                                               _d(out)))
+        return out
+
+    # -- EulerUpstreamResidual::computeCapPressures (:459-467) / computeCapPressure (SimulatorUtilities.hpp:219-230)
+    def computeCapPressures(self, saturation):
+        s = np.ascontiguousarray(saturation, dtype=np.float64)
+        out = np.zeros(self.L.eu_local_cells(self.h))
+        self._check(self.L.eu_compute_cap_pressures(self.h, _d(s), _d(out)))
+        return out
+
+    # -- diagnostics (SimulatorUtilities.hpp:59-86, :153-170, :273-279) on the resident fluxes
+    def cellVelocity(self):
+        out = np.zeros((self.L.eu_local_cells(self.h), 3))
+        self._check(self.L.eu_cell_velocity(self.h, _d(out)))
+        return out
+
+    def phaseVelocities(self, saturation=None, cell_velocity=None):
+        n = self.L.eu_local_cells(self.h)
+        s = None if saturation is None else np.ascontiguousarray(saturation, dtype=np.float64)
+        cv = None if cell_velocity is None else np.ascontiguousarray(cell_velocity, dtype=np.float64)
+        vw, vo = np.zeros((n, 3)), np.zeros((n, 3))
+        self._check(self.L.eu_phase_velocities(self.h, None if s is None else _d(s), None if cv is None else _d(cv), _d(vw), _d(vo)))
+        return vw, vo
+
+    def fractionalFlow(self, saturation=None):
+        s = None if saturation is None else np.ascontiguousarray(saturation, dtype=np.float64)
+        out = np.zeros(self.L.eu_local_cells(self.h))
+        self._check(self.L.eu_fractional_flow(self.h, None if s is None else _d(s), _d(out)))
+        return out
 
     @staticmethod
     def _sources(inj):

@@ -460,6 +460,48 @@ int eo_small_step(const eo_case* c, double* sat, double dt, const double* gravit
     return 0;
 }
 
+/* ---------------------------------------------------------------------------------
+ * Diagnostics the drivers run right after transport (common/SimulatorUtilities.hpp).
+ * --------------------------------------------------------------------------------- */
+/* estimateCellVelocity, SimulatorUtilities.hpp:59-86: per face v = centroid(f); v -= centroid(c);
+ * v *= flux/volume; cell_v += v.  out: 3 doubles per cell. */
+void eo_cell_velocity(const eo_case* c, const double* hf_flux, double* out)
+{
+    for (int cell = 0; cell < c->N; ++cell) {
+        double cv[3] = { 0.0, 0.0, 0.0 };
+        for (int hf = c->hf_offset[cell]; hf < c->hf_offset[cell + 1]; ++hf) {
+            const double s = hf_flux[hf]/c->cell_volume[cell];
+            for (int d = 0; d < 3; ++d) {
+                double v = c->hf_centroid[3*(size_t)hf + d];
+                v -= c->cell_centroid[3*(size_t)cell + d];
+                v *= s;
+                cv[d] += v;
+            }
+        }
+        for (int d = 0; d < 3; ++d) out[3*(size_t)cell + d] = cv[d];
+    }
+}
+
+/* computePhaseVelocities, SimulatorUtilities.hpp:153-170: v_w = v*f, v_o = v*(1.0 - f), f = rp.fractionalFlow */
+void eo_phase_velocities(const eo_case* c, const double* sat, const double* cell_velocity, double* vw, double* vo)
+{
+    for (int cell = 0; cell < c->N; ++cell) {
+        const double f = eo_fractional_flow(c, cell, sat[cell]);
+        const double omf = 1.0 - f;
+        for (int d = 0; d < 3; ++d) {
+            const double v = cell_velocity[3*(size_t)cell + d];
+            vw[3*(size_t)cell + d] = v*f;
+            vo[3*(size_t)cell + d] = v*omf;
+        }
+    }
+}
+
+/* computeCapPressure, SimulatorUtilities.hpp:219-230 == EulerUpstreamResidual::computeCapPressures (:459-467) */
+void eo_cap_pressures(const eo_case* c, const double* sat, double* out)
+{
+    for (int cell = 0; cell < c->N; ++cell) out[cell] = eo_cap_pressure(c, cell, sat[cell]);
+}
+
 /* CflCalculator.hpp:54-83 */
 int eo_cfl_velocity(const eo_case* c, const double* hf_flux, double* dt_out)
 {

@@ -89,6 +89,10 @@ double eo_cfl_gravity(const eo_case* c, const double* gravity);
 double eo_cfl_capillary(const eo_case* c);
 void eo_transport_solve(const eo_case* c, double* sat, double time, const double* gravity, const double* hf_flux,
                         int n_src, const int* src_cell, const double* src_rate, eo_result* out);
+/* diagnostics (common/SimulatorUtilities.hpp:59-86, :153-170, :219-230); vectors are 3 doubles per cell */
+void eo_cell_velocity(const eo_case* c, const double* hf_flux, double* out);
+void eo_phase_velocities(const eo_case* c, const double* sat, const double* cell_velocity, double* vw, double* vo);
+void eo_cap_pressures(const eo_case* c, const double* sat, double* out);
 /* ReservoirPropertyCapillary<3>::computeCflFactors restated (kind 0 only) */
 void eo_compute_cfl_factors(const eo_case* c, double* out3);
 

@@ -158,6 +158,38 @@ class RefSolver:
         self.lib.ref_cfl_factors(self.h, _d(out))
         return out
 
+    def compute_residual(self, sat, methods, gravity=None, hf_flux=None, src_cell=None, src_rate=None):
+        """EulerUpstreamResidual::computeResidual with explicit (viscous, gravity, capillary) flags."""
+        c = self.case
+        sat = np.ascontiguousarray(sat, dtype=np.float64)
+        g = np.asarray(c.gravity if gravity is None else gravity, dtype=np.float64)
+        fl = np.ascontiguousarray(c.hf_flux if hf_flux is None else hf_flux, dtype=np.float64)
+        sc = c.src_cell if src_cell is None else np.ascontiguousarray(src_cell, dtype=np.int32)
+        sr = c.src_rate if src_rate is None else np.ascontiguousarray(src_rate, dtype=np.float64)
+        out = np.zeros(c.N)
+        self.lib.ref_compute_residual(self.h, _d(sat), _d(g), _d(fl), C.c_int(sc.shape[0]), _i(sc), _d(sr),
+                                      C.c_int(int(methods[0])), C.c_int(int(methods[1])), C.c_int(int(methods[2])), _d(out))
+        return out
+
+    def cell_velocity(self, hf_flux=None):
+        fl = np.ascontiguousarray(self.case.hf_flux if hf_flux is None else hf_flux, dtype=np.float64)
+        out = np.zeros((self.case.N, 3))
+        self.lib.ref_cell_velocity(self.h, _d(fl), _d(out))
+        return out
+
+    def phase_velocities(self, sat, cell_velocity):
+        sat = np.ascontiguousarray(sat, dtype=np.float64)
+        cv = np.ascontiguousarray(cell_velocity, dtype=np.float64)
+        vw, vo = np.zeros_like(cv), np.zeros_like(cv)
+        self.lib.ref_phase_velocities(self.h, _d(sat), _d(cv), _d(vw), _d(vo))
+        return vw, vo
+
+    def cap_pressures(self, sat):
+        sat = np.ascontiguousarray(sat, dtype=np.float64)
+        out = np.zeros(self.case.N)
+        self.lib.ref_cap_pressures(self.h, _d(sat), _d(out))
+        return out
+
     def cap_pressure(self, cell, s):
         return self.lib.ref_cap_pressure(self.h, int(cell), float(s))
 
@@ -279,6 +311,43 @@ class PortSolver:
         st = self.lib.eo_small_step(C.byref(self.ec), _d(sat), C.c_double(dt), _d(g), _d(fl), C.c_int(sc.shape[0]),
                                     _i(sc), _d(sr), _d(cap), _d(res), C.byref(bc), C.byref(bv))
         return dict(sat=sat, residual=res, status=st, bad_cell=bc.value, bad_value=bv.value, cap=cap)
+
+    def compute_residual(self, sat, methods, gravity=None, hf_flux=None, src_cell=None, src_rate=None):
+        """eo_compute_residual with explicit (viscous, gravity, capillary) flags; the case's own flags are restored."""
+        c = self.case
+        sat = np.ascontiguousarray(sat, dtype=np.float64)
+        g, fl, sc, sr = self._inputs(gravity, hf_flux, src_cell, src_rate)
+        ec = self.ec
+        saved = (ec.method_viscous, ec.method_gravity, ec.method_capillary)
+        ec.method_viscous, ec.method_gravity, ec.method_capillary = (int(bool(m)) for m in methods)
+        cap, res = np.zeros(c.N), np.zeros(c.N)
+        try:
+            self.lib.eo_compute_residual(C.byref(ec), _d(sat), _d(g), _d(fl), C.c_int(sc.shape[0]), _i(sc), _d(sr), _d(cap), _d(res))
+        finally:
+            ec.method_viscous, ec.method_gravity, ec.method_capillary = saved
+        return res
+
+    def cell_velocity(self, hf_flux=None):
+        fl = np.ascontiguousarray(self.case.hf_flux if hf_flux is None else hf_flux, dtype=np.float64)
+        out = np.zeros((self.case.N, 3))
+        self.lib.eo_cell_velocity(C.byref(self.ec), _d(fl), _d(out))
+        return out
+
+    def phase_velocities(self, sat, cell_velocity):
+        sat = np.ascontiguousarray(sat, dtype=np.float64)
+        cv = np.ascontiguousarray(cell_velocity, dtype=np.float64)
+        vw, vo = np.zeros_like(cv), np.zeros_like(cv)
+        self.lib.eo_phase_velocities(C.byref(self.ec), _d(sat), _d(cv), _d(vw), _d(vo))
+        return vw, vo
+
+    def cap_pressures(self, sat):
+        sat = np.ascontiguousarray(sat, dtype=np.float64)
+        out = np.zeros(self.case.N)
+        self.lib.eo_cap_pressures(C.byref(self.ec), _d(sat), _d(out))
+        return out
+
+    def frac_flows(self, sat):
+        return np.array([self.frac_flow(c, s) for c, s in enumerate(np.asarray(sat, dtype=np.float64))])
 
     def cfl_times(self, gravity=None, hf_flux=None):
         g, fl, _, _ = self._inputs(gravity, hf_flux, None, None)

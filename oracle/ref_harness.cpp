@@ -14,6 +14,7 @@
 #include <opm/porsol/common/ReservoirPropertyCapillaryAnisotropicRelperm.hpp>
 #endif
 #include <opm/porsol/common/BoundaryConditions.hpp>
+#include <opm/porsol/common/SimulatorUtilities.hpp>
 
 #include "FlatGrid.hpp"
 
@@ -69,6 +70,14 @@ namespace {
         virtual void mobility(int phase, int cell, double s, double* out9) const = 0;
         virtual double fracFlow(int cell, double s) const = 0;
         virtual double porosity(int cell) const = 0;
+        // EulerUpstreamResidual::computeResidual with explicit method flags (Residual_impl.hpp:472-505)
+        virtual void computeResidual(const std::vector<double>& sat, const GI::Vector& g, const FlatFlux& flux,
+                                     const Opm::SparseVector<double>& inj, bool mv, bool mg, bool mc,
+                                     std::vector<double>& out) = 0;
+        // SimulatorUtilities.hpp:153-170, :219-230
+        virtual void phaseVelocities(const std::vector<double>& sat, const std::vector<GI::Vector>& cv,
+                                     std::vector<GI::Vector>& vw, std::vector<GI::Vector>& vo) const = 0;
+        virtual void capPressures(const std::vector<double>& sat, std::vector<double>& out) const = 0;
     };
 
     template <class RP> struct MobOut;
@@ -181,6 +190,22 @@ namespace {
         void mobility(int phase, int cell, double s, double* out9) const { MobOut<RP>::get(rp, phase, cell, s, out9); }
         double fracFlow(int cell, double s) const { return rp.fractionalFlow(cell, s); }
         double porosity(int cell) const { return rp.porosity(cell); }
+        void computeResidual(const std::vector<double>& sat, const GI::Vector& g, const FlatFlux& flux,
+                             const Opm::SparseVector<double>& inj, bool mv, bool mg, bool mc, std::vector<double>& out)
+        {
+            // like smallTimeStep (EulerUpstream_impl.hpp:362-369): the cached capillary pressures first
+            if (mc) solver.residual_computer_.computeCapPressures(sat);
+            solver.residual_computer_.computeResidual(sat, g, flux, inj, mv, mg, mc, out);
+        }
+        void phaseVelocities(const std::vector<double>& sat, const std::vector<GI::Vector>& cv,
+                             std::vector<GI::Vector>& vw, std::vector<GI::Vector>& vo) const
+        {
+            Opm::computePhaseVelocities(vw, vo, rp, sat, cv);
+        }
+        void capPressures(const std::vector<double>& sat, std::vector<double>& out) const
+        {
+            Opm::computeCapPressure(out, rp, sat);
+        }
     };
 
     void writeTable(const std::string& fname, int npts, int ncol, const double* const* cols)
@@ -382,6 +407,50 @@ void ref_cfl_times(void* hv, const double* gravity, const double* hf_flux, doubl
     HarnessBase* h = static_cast<HarnessBase*>(hv);
     FlatFlux flux = { hf_flux };
     h->cflTimes(vec3(gravity), flux, out3, total);
+}
+
+void ref_compute_residual(void* hv, const double* sat, const double* gravity, const double* hf_flux,
+                          int n_src, const int* src_cell, const double* src_rate, int mv, int mg, int mc, double* out)
+{
+    HarnessBase* h = static_cast<HarnessBase*>(hv);
+    const int N = h->grid.numberOfCells();
+    std::vector<double> s(sat, sat + N), res;
+    FlatFlux flux = { hf_flux };
+    Opm::SparseVector<double> inj = makeInj(N, n_src, src_cell, src_rate);
+    h->computeResidual(s, vec3(gravity), flux, inj, mv != 0, mg != 0, mc != 0, res);
+    std::copy(res.begin(), res.end(), out);
+}
+
+// estimateCellVelocity (SimulatorUtilities.hpp:59-86); out: 3 doubles per cell
+void ref_cell_velocity(void* hv, const double* hf_flux, double* out)
+{
+    HarnessBase* h = static_cast<HarnessBase*>(hv);
+    FlatFlux flux = { hf_flux };
+    std::vector<GI::Vector> cv;
+    Opm::estimateCellVelocity(cv, h->grid, flux);
+    for (size_t c = 0; c < cv.size(); ++c) for (int d = 0; d < 3; ++d) out[3*c + d] = cv[c][d];
+}
+
+// computePhaseVelocities (SimulatorUtilities.hpp:153-170)
+void ref_phase_velocities(void* hv, const double* sat, const double* cell_velocity, double* vw_out, double* vo_out)
+{
+    HarnessBase* h = static_cast<HarnessBase*>(hv);
+    const int N = h->grid.numberOfCells();
+    std::vector<double> s(sat, sat + N);
+    std::vector<GI::Vector> cv(N), vw, vo;
+    for (int c = 0; c < N; ++c) for (int d = 0; d < 3; ++d) cv[c][d] = cell_velocity[3*c + d];
+    h->phaseVelocities(s, cv, vw, vo);
+    for (int c = 0; c < N; ++c) for (int d = 0; d < 3; ++d) { vw_out[3*c + d] = vw[c][d]; vo_out[3*c + d] = vo[c][d]; }
+}
+
+// computeCapPressure (SimulatorUtilities.hpp:219-230)
+void ref_cap_pressures(void* hv, const double* sat, double* out)
+{
+    HarnessBase* h = static_cast<HarnessBase*>(hv);
+    const int N = h->grid.numberOfCells();
+    std::vector<double> s(sat, sat + N), pc;
+    h->capPressures(s, pc);
+    std::copy(pc.begin(), pc.end(), out);
 }
 
 void ref_cfl_factors(void* hv, double* out3) { static_cast<HarnessBase*>(hv)->cflFactors(out3); }
