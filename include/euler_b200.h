@@ -53,7 +53,8 @@ enum { EU_MOB_SCALAR = 0, EU_MOB_DIAGONAL = 1 };
 
 /* arithmetic modes */
 enum {
-    EU_MODE_AUTO = 0,    /* fast where implemented (scalar mobility), strict otherwise */
+    EU_MODE_AUTO = 0,    /* fast where implemented (scalar mobility; diagonal tensor mobility on grids whose face
+                            normals are axis-aligned), strict otherwise */
     EU_MODE_STRICT = 1,  /* reference operation order, no FMA contraction: bit-identical to the reference */
     EU_MODE_FAST = 2     /* static per-face quantities pre-contracted to scalars, FMA allowed:
                             |dS| error ~1e-16 per substep (gate: 1e-12), identical step counts */
@@ -170,6 +171,9 @@ int eu_grid_end(eu_handle h);               /* builds the device structures */
 /* number of local cells / half-faces held by this rank, in upload order (own + ghost) */
 int eu_local_cells(eu_handle h);
 long long eu_local_halffaces(eu_handle h);
+/* the arithmetic mode in effect after eu_grid_end: EU_MODE_STRICT or EU_MODE_FAST (EU_MODE_AUTO resolves to FAST for
+ * the scalar mobility class and for the diagonal tensor class on grids with axis-aligned face normals, else STRICT) */
+int eu_resolved_mode(eu_handle h);
 /* fraction of (slice, slot) pairs whose adjacency is described by an 8-byte descriptor instead of 32 records */
 double eu_regular_fraction(eu_handle h);
 

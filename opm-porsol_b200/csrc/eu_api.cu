@@ -85,6 +85,12 @@ struct eu_solver {
     int n_buckets = 0;
     bool fast_tables_ok = true;
     EuTablesDev tab;
+    // FAST curve sets: one per rock (scalar mobility) or three per rock, x/y/z (diagonal tensor mobility on grids with
+    // axis-aligned face normals); tabf is `tab` with the set count / offsets of the FAST tables
+    EuTablesDev tabf;
+    DevBuf<int> d_tab_offset_fast;
+    bool tensor_fast = false;
+    DevBuf<unsigned char> d_axis8;
     // ---- derived
     DevBuf<int> d_owner_hf, d_fid_of_hf, d_slice_base, d_flags;
     DevBuf<int2> d_strict_list, d_rec, d_desc;
@@ -168,6 +174,7 @@ struct eu_solver {
         f.classes = d_classes.p; f.n_classes = n_classes; f.slice_base = d_slice_base.p; f.rec = d_rec.p; f.desc = d_desc.p;
         f.qg = d_qg.p; f.T = d_T.p; f.nn = use_nn ? d_nn.p : nullptr;
         f.inv_porevol = d_inv_porevol.p; f.pcscale = d_pcscale.p; f.rock8 = d_rock8.p; f.F = F;
+        f.axis8 = tensor_fast ? d_axis8.p : nullptr;
         f.prefetch = prefetch;
         return f;
     }
@@ -251,6 +258,12 @@ void set_tables_struct(eu_handle h)
     t.inv_visc[0] = 1.0/h->fluid.viscosity[0]; t.inv_visc[1] = 1.0/h->fluid.viscosity[1];
     t.n_buckets = h->n_buckets;
     t.fcoef = h->d_fcoef.p; t.fjcoef = h->d_fjcoef.p; t.fxb = h->d_fxb.p; t.fbucket = h->d_fbucket.p;
+    // the view the FAST kernels get: curve sets instead of rocks
+    h->tabf = t;
+    const int reps = h->fluid.mobility_kind == EU_MOB_DIAGONAL ? 3 : 1;
+    h->tabf.n_rocks = h->fluid.n_rocks*reps;
+    h->tabf.n_nodes_total = int(h->d_fxb.n);
+    h->tabf.offset = h->d_tab_offset_fast.p;
 }
 
 int ensure_contracted(eu_handle h, const double gravity[3])
@@ -347,7 +360,7 @@ int build_items(eu_handle h, int lo, int hi)
     const char* env_noclass = getenv("EU_NO_CLASSES");
     // the marches read the neighbours' stored mobilities, which exist for own cells only: slice classes are used when
     // no item touches a ghost cell (one rank, or the fused exchange whose boundary ranges take the generic path)
-    const bool use_classes = !(env_noclass && atoi(env_noclass) != 0) && (h->cfg.world_size <= 1 || fused_halo(h));
+    const bool use_classes = !(env_noclass && atoi(env_noclass) != 0) && (h->cfg.world_size <= 1 || fused_halo(h)) && !h->tensor_fast;
     for (int s = lo; s < hi && use_classes; ++s) {
         if (s*EU_SLICE < h->own_lo || (s + 1)*EU_SLICE > h->own_hi) continue;
         const int width = (base[size_t(s) + 1] - base[size_t(s)])/EU_SLICE;
@@ -526,7 +539,7 @@ int launch_substep(eu_handle h, const EuStepArgs& a, bool exchange)
             halo.timeout_cycles = 20000000000LL;
             halo.err_flag = h->d_flags.p + 3;
         }
-        eu_launch_fast_step(g, h->tab, h->fast(), a, halo, slice_lo, slice_hi, h->n_sms, h->st);
+        eu_launch_fast_step(g, h->tabf, h->fast(), a, halo, slice_lo, slice_hi, h->n_sms, h->st);
         return 1;
     }
     int launches = 1;
@@ -810,29 +823,43 @@ int eu_set_fluid(eu_handle h, const eu_fluid* f)
     if ((rc = upload_vec(h, h->d_tab_offset, h->h_tab_offset))) return rc;
     if ((rc = upload_vec(h, h->d_tab_s, h->h_tab_s))) return rc;
     for (int k = 0; k < 7; ++k) if ((rc = upload_vec(h, h->d_tab_cols[k], h->h_tab_cols[k]))) return rc;
-    // FAST tables (scalar mobility): mobility = kr/viscosity and J per interval in intercept/slope form
+    // FAST tables: mobility = kr/viscosity and J (or pc) per interval in intercept/slope form, one curve set per rock
+    // (scalar mobility: krw, kro, J) or per rock and axis (diagonal tensor mobility: kr??_w, kr??_o, pc)
     h->fast_tables_ok = true;
     h->n_buckets = 0;
-    if (f->mobility_kind == EU_MOB_SCALAR && f->n_rocks > 0) {
-        const int nn = int(h->h_tab_s.size());
+    const bool tensor = f->mobility_kind == EU_MOB_DIAGONAL;
+    const int reps = tensor ? 3 : 1;
+    std::vector<int> off_fast(1, 0);
+    if (f->n_rocks > 0 && f->n_rocks*reps > EU_MAX_TABLES) h->fast_tables_ok = false;
+    if (f->n_rocks > 0 && h->fast_tables_ok) {
         const double inf = std::numeric_limits<double>::infinity();
-        std::vector<double> coef(size_t(4)*nn, 0.0), jcoef(size_t(2)*nn, 0.0), xb(h->h_tab_s);
+        std::vector<double> coef, jcoef, xb;
         for (int r = 0; r < f->n_rocks; ++r) {
             const int b = h->h_tab_offset[r], e = h->h_tab_offset[r + 1];
-            for (int i = b; i + 1 < e; ++i) {
-                const double x0 = h->h_tab_s[i], dx = h->h_tab_s[i + 1] - x0;
-                if (!(dx > 0.0)) return fail(h, EU_ERR_ARG, "rock table saturations must be strictly increasing");
-                for (int p = 0; p < 2; ++p) {
-                    const double y0 = h->h_tab_cols[p][i]/f->viscosity[p], y1 = h->h_tab_cols[p][i + 1]/f->viscosity[p];
-                    const double slope = (y1 - y0)/dx;
-                    coef[size_t(4)*i + 2*p] = y0 - slope*x0;
-                    coef[size_t(4)*i + 2*p + 1] = slope;
+            for (int ax = 0; ax < reps; ++ax) {
+                const std::vector<double>* col[3] = { &h->h_tab_cols[tensor ? 1 + ax : 0], &h->h_tab_cols[tensor ? 4 + ax : 1],
+                                                      &h->h_tab_cols[tensor ? 0 : 2] };
+                const size_t o = xb.size();
+                coef.resize(4*(o + size_t(e - b)), 0.0);
+                jcoef.resize(2*(o + size_t(e - b)), 0.0);
+                for (int i = b; i < e; ++i) xb.push_back(h->h_tab_s[i]);
+                for (int i = b; i + 1 < e; ++i) {
+                    const double x0 = h->h_tab_s[i], dx = h->h_tab_s[i + 1] - x0;
+                    if (!(dx > 0.0)) return fail(h, EU_ERR_ARG, "rock table saturations must be strictly increasing");
+                    const size_t k = o + size_t(i - b);
+                    for (int p = 0; p < 2; ++p) {
+                        const double y0 = (*col[p])[i]/f->viscosity[p], y1 = (*col[p])[i + 1]/f->viscosity[p];
+                        const double slope = (y1 - y0)/dx;
+                        coef[4*k + 2*p] = y0 - slope*x0;
+                        coef[4*k + 2*p + 1] = slope;
+                    }
+                    const double j0 = (*col[2])[i], slope = ((*col[2])[i + 1] - j0)/dx;
+                    jcoef[2*k] = j0 - slope*x0;
+                    jcoef[2*k + 1] = slope;
                 }
-                const double j0 = h->h_tab_cols[2][i], slope = (h->h_tab_cols[2][i + 1] - j0)/dx;
-                jcoef[size_t(2)*i] = j0 - slope*x0;
-                jcoef[size_t(2)*i + 1] = slope;
+                xb.back() = inf;
+                off_fast.push_back(int(xb.size()));
             }
-            xb[size_t(e) - 1] = inf;
         }
         // buckets over [0,1): smallest power of two such that no bucket holds two interior nodes
         int nb = 64;
@@ -854,11 +881,13 @@ int eu_set_fluid(eu_handle h, const eu_fluid* f)
             h->fast_tables_ok = false;          // nodes closer than 1/4096: FAST search not applicable
         } else {
             h->n_buckets = nb;
-            std::vector<unsigned char> bucket(size_t(f->n_rocks)*nb, 0);
+            const int sets = f->n_rocks*reps;
+            std::vector<unsigned char> bucket(size_t(sets)*nb, 0);
             for (int r = 0; r < f->n_rocks; ++r) {
                 const int b = h->h_tab_offset[r], e = h->h_tab_offset[r + 1];
-                for (int k = 1; k < nb; ++k)
-                    bucket[size_t(r)*nb + k] = (unsigned char)table_index_host(&h->h_tab_s[b], e - b, double(k)/nb);
+                for (int ax = 0; ax < reps; ++ax)
+                    for (int k = 1; k < nb; ++k)
+                        bucket[size_t(r*reps + ax)*nb + k] = (unsigned char)table_index_host(&h->h_tab_s[b], e - b, double(k)/nb);
             }
             if ((rc = upload_vec(h, h->d_fbucket, bucket))) return rc;
             if ((rc = upload_vec(h, h->d_fcoef, coef))) return rc;
@@ -866,15 +895,20 @@ int eu_set_fluid(eu_handle h, const eu_fluid* f)
             if ((rc = upload_vec(h, h->d_fxb, xb))) return rc;
         }
     }
+    if ((rc = upload_vec(h, h->d_tab_offset_fast, off_fast))) return rc;
     set_tables_struct(h);
     h->fluid_set = true;
     h->contracted = false;
     h->cfl_cap_valid = h->cfl_grav_valid = false;
+    // arithmetic mode.  Tensor mobility: FAST needs axis-aligned face normals, decided in eu_grid_end once the grid is
+    // there (AUTO falls back to STRICT, an explicit FAST request fails); without rock tables the tensor class is
+    // isotropic (RockAnisotropicRelperm / ..._impl.hpp:86-101: the same quadratic curve in every direction) and runs
+    // the scalar FAST path.
+    h->tensor_fast = false;
     if (h->cfg.mode == EU_MODE_STRICT) h->mode = EU_MODE_STRICT;
-    else if (f->mobility_kind == EU_MOB_SCALAR && h->fast_tables_ok) h->mode = EU_MODE_FAST;
-    else if (f->mobility_kind == EU_MOB_SCALAR && h->cfg.mode == EU_MODE_FAST)
-        return fail(h, EU_ERR_UNSUPPORTED, "FAST mode needs rock-table nodes at least 1/4096 apart");
-    else if (h->cfg.mode == EU_MODE_FAST) return fail(h, EU_ERR_UNSUPPORTED, "FAST mode implements scalar mobility only");
+    else if (h->fast_tables_ok) { h->mode = EU_MODE_FAST; h->tensor_fast = tensor && f->n_rocks > 0; }
+    else if (h->cfg.mode == EU_MODE_FAST)
+        return fail(h, EU_ERR_UNSUPPORTED, "FAST mode needs rock-table nodes at least 1/4096 apart and at most 48 curve sets");
     else h->mode = EU_MODE_STRICT;
     return EU_OK;
 }
@@ -950,6 +984,21 @@ int eu_grid_end(eu_handle h)
     if (flags[0] == 2) return fail(h, EU_ERR_ARG, "periodic partner cell of an own cell was not uploaded");
     if (flags[0] == 3) return fail(h, EU_ERR_ARG, "neighbour (ghost) cell of an own cell was not uploaded");
 
+    if (h->tensor_fast) {
+        // FAST with diagonal tensor mobility needs axis-aligned face normals
+        int not_aligned = 0;
+        EU_CUDA(h, cudaMemsetAsync(h->d_flags.p, 0, 4*sizeof(int), h->st));
+        eu_launch_axis_check(g, h->d_flags.p, h->st);
+        EU_CUDA(h, cudaMemcpyAsync(&not_aligned, h->d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+        EU_CUDA(h, cudaStreamSynchronize(h->st));
+        EU_CUDA(h, cudaGetLastError());
+        if (not_aligned) {
+            if (h->cfg.mode == EU_MODE_FAST)
+                return fail(h, EU_ERR_UNSUPPORTED, "FAST mode with tensor mobility needs axis-aligned face normals");
+            h->tensor_fast = false;
+            h->mode = EU_MODE_STRICT;
+        }
+    }
     EU_CUDA(h, h->d_fid_of_hf.alloc(H));
     if (h->mode == EU_MODE_STRICT) {
         EU_CUDA(h, h->d_strict_list.alloc(H));
@@ -997,6 +1046,11 @@ int eu_grid_end(eu_handle h)
         EU_CUDA(h, h->d_T.alloc(F));
         EU_CUDA(h, cudaMemsetAsync(h->d_qg.p, 0, F*sizeof(double2), h->st));
         EU_CUDA(h, cudaMemsetAsync(h->d_T.p, 0, F*sizeof(double), h->st));
+        if (h->tensor_fast) {
+            EU_CUDA(h, h->d_axis8.alloc(F));
+            EU_CUDA(h, cudaMemsetAsync(h->d_axis8.p, 0, F, h->st));
+            eu_launch_face_axis(g, h->d_owner_hf.p, h->d_fid_of_hf.p, h->d_axis8.p, h->st);
+        }
         EU_CUDA(h, h->d_pcscale.alloc(n));
         EU_CUDA(h, h->d_rock8.alloc(n));
         EU_CUDA(h, h->d_inv_porevol.alloc(n));
@@ -1028,6 +1082,7 @@ int eu_grid_end(eu_handle h)
 }
 
 int eu_local_cells(eu_handle h) { return h ? h->n_local : 0; }
+int eu_resolved_mode(eu_handle h) { return (h && h->grid_ready) ? h->mode : EU_MODE_AUTO; }
 double eu_regular_fraction(eu_handle h) { return h ? h->regular_fraction : 0.0; }
 long long eu_local_halffaces(eu_handle h) { return h ? h->H : 0; }
 
@@ -1092,7 +1147,7 @@ int eu_small_step(eu_handle h, double dt, const double gravity[3], int n_src, co
     const unsigned long long none = ~0ULL;
     EU_CUDA(h, cudaMemcpyAsync(h->d_fail_key.p, &none, sizeof(none), cudaMemcpyHostToDevice, h->st));
     if (h->mode == EU_MODE_FAST)
-        eu_launch_fast_state(h->grid(), h->tab, h->fast(), h->d_S[h->cur].p, h->par.method_capillary ? h->d_pc[h->cur].p : nullptr,
+        eu_launch_fast_state(h->grid(), h->tabf, h->fast(), h->d_S[h->cur].p, h->par.method_capillary ? h->d_pc[h->cur].p : nullptr,
                              h->d_lam[h->cur].p, 0, h->n_local, h->st);
     EuStepArgs a = step_args(h, dt, gravity, nls, 0);
     a.residual_out = h->d_residual.p;
@@ -1157,7 +1212,7 @@ int eu_compute_residual(eu_handle h, const double* saturation, const double grav
         cudaMemcpyAsync(h->d_fail_key.p, &none, sizeof(none), cudaMemcpyHostToDevice, h->st);
         h->cur = in;
         if (h->mode == EU_MODE_FAST)
-            eu_launch_fast_state(h->grid(), h->tab, h->fast(), h->d_S[in].p, method_capillary ? h->d_pc[in].p : nullptr,
+            eu_launch_fast_state(h->grid(), h->tabf, h->fast(), h->d_S[in].p, method_capillary ? h->d_pc[in].p : nullptr,
                                  h->d_lam[in].p, 0, h->n_local, h->st);
         EuStepArgs a = step_args(h, 0.0, gravity, nls, 0);
         a.residual_out = h->d_residual.p;
@@ -1318,7 +1373,7 @@ int eu_transport_solve_resident(eu_handle h, double time, const double gravity[3
         ++rep->attempts;
         EU_CUDA(h, cudaMemcpyAsync(h->d_fail_key.p, &none, sizeof(none), cudaMemcpyHostToDevice, h->st));
         if (h->mode == EU_MODE_FAST) {
-            eu_launch_fast_state(h->grid(), h->tab, h->fast(), h->d_S[h->cur].p, p.method_capillary ? h->d_pc[h->cur].p : nullptr,
+            eu_launch_fast_state(h->grid(), h->tabf, h->fast(), h->d_S[h->cur].p, p.method_capillary ? h->d_pc[h->cur].p : nullptr,
                                  h->d_lam[h->cur].p, 0, h->n_local, h->st);
             ++launches;
         }

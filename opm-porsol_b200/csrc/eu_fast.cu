@@ -41,7 +41,7 @@ struct TabLayout {
     __device__ __forceinline__ const double2* jcoef() const { return reinterpret_cast<const double2*>(eu_smem + size_t(32)*nn); }
     __device__ __forceinline__ const double* xb() const { return reinterpret_cast<const double*>(eu_smem + size_t(48)*nn); }
     __device__ __forceinline__ const int* offset() const { return reinterpret_cast<const int*>(eu_smem + size_t(56)*nn); }
-    __device__ __forceinline__ const unsigned char* bucket() const { return eu_smem + size_t(56)*nn + 4*(EU_MAX_ROCKS + 2); }
+    __device__ __forceinline__ const unsigned char* bucket() const { return eu_smem + size_t(56)*nn + 4*(EU_MAX_TABLES + 2); }
 };
 
 __device__ __forceinline__ void tables_to_smem(const EuTablesDev& t)
@@ -51,7 +51,7 @@ __device__ __forceinline__ void tables_to_smem(const EuTablesDev& t)
     double2* jc = reinterpret_cast<double2*>(eu_smem + size_t(32)*nn);
     double* xb = reinterpret_cast<double*>(eu_smem + size_t(48)*nn);
     int* off = reinterpret_cast<int*>(eu_smem + size_t(56)*nn);
-    unsigned char* bucket = eu_smem + size_t(56)*nn + 4*(EU_MAX_ROCKS + 2);
+    unsigned char* bucket = eu_smem + size_t(56)*nn + 4*(EU_MAX_TABLES + 2);
     for (int i = threadIdx.x; i < nn; i += blockDim.x) {
         coef[i] = make_double4(t.fcoef[4*i], t.fcoef[4*i + 1], t.fcoef[4*i + 2], t.fcoef[4*i + 3]);
         jc[i] = make_double2(t.fjcoef[2*i], t.fjcoef[2*i + 1]);
@@ -197,11 +197,35 @@ __device__ __forceinline__ double cap_coefficient(const TabLayout& L, const EuTa
     return div_pos(lwa*loa, lwa + loa);
 }
 
-template <bool ROCKS, bool MULTIROCK, bool CAP, bool NN, int W, int B>
+// Diagonal tensor mobility (TENSOR, ReservoirPropertyCapillaryAnisotropicRelperm): FAST mode covers grids whose face
+// normals are axis-aligned.  Then every term of the face flux (Residual_impl.hpp:205-262) reduces to the scalar
+// formula with the mobility component of the face's axis: n.(M x) = n_a m_a x_a.  The curves of (rock r, axis a) are
+// stored as table 3 r + a, the own cell's mobilities come per axis (OwnMob), the face's axis from f.axis8.
+template <bool TENSOR>
+struct OwnMob {
+    double lw[TENSOR ? 3 : 1], lo[TENSOR ? 3 : 1];
+    __device__ __forceinline__ double w(int ax) const { return TENSOR ? (ax == 0 ? lw[0] : (ax == 1 ? lw[TENSOR ? 1 : 0] : lw[TENSOR ? 2 : 0])) : lw[0]; }
+    __device__ __forceinline__ double o(int ax) const { return TENSOR ? (ax == 0 ? lo[0] : (ax == 1 ? lo[TENSOR ? 1 : 0] : lo[TENSOR ? 2 : 0])) : lo[0]; }
+};
+
+template <bool ROCKS, bool MULTIROCK, bool TENSOR>
+__device__ __forceinline__ OwnMob<TENSOR> own_mobilities(const TabLayout& L, const EuTablesDev& t, int rock0, double S0)
+{
+    OwnMob<TENSOR> m;
+    if (TENSOR) {
+#pragma unroll
+        for (int ax = 0; ax < (TENSOR ? 3 : 1); ++ax) Mob<ROCKS, MULTIROCK>::both(L, t, 3*rock0 + ax, S0, m.lw[ax], m.lo[ax]);
+    } else {
+        Mob<ROCKS, MULTIROCK>::both(L, t, rock0, S0, m.lw[0], m.lo[0]);
+    }
+    return m;
+}
+
+template <bool ROCKS, bool MULTIROCK, bool CAP, bool NN, int W, int B, bool TENSOR>
 __device__ __forceinline__ double gather_cell(const TabLayout& L, const EuGridDev& g, const EuTablesDev& t,
                                               const EuFastDev& f, const EuStepArgs& a, const int2* __restrict__ recp,
                                               const int2* __restrict__ dscp, int width, int c, double S0, int rock0, double pc0,
-                                              double lw0, double lo0)
+                                              const OwnMob<TENSOR>& own0)
 {
     // phase A: the cell's records.  Regular slots come from the 8-byte slice descriptor (neighbour = c + d,
     // face id affine in c): no per-cell record is read; irregular slots (boundaries, faults) load theirs.
@@ -231,6 +255,7 @@ __device__ __forceinline__ double gather_cell(const TabLayout& L, const EuGridDe
         double S1[B], T[CAP ? B : 1], pc1[CAP ? B : 1], nn[NN ? B : 1];
         double2 qg[B];
         int rk[MULTIROCK ? B : 1];
+        int ax[TENSOR ? B : 1];
 #pragma unroll
         for (int k = 0; k < B; ++k) {
             const int j = j0 + k;
@@ -238,9 +263,11 @@ __device__ __forceinline__ double gather_cell(const TabLayout& L, const EuGridDe
             if (CAP) { T[k] = 0.0; pc1[k] = 0.0; }
             if (NN) nn[k] = 1.0;
             if (MULTIROCK) rk[k] = rock0;
+            if (TENSOR) ax[k] = 0;
             if (j < W && r[j].x != EU_REC_PAD) {
                 qg[k] = __ldg(f.qg + r[j].y);
                 if (NN) nn[k] = __ldg(f.nn + r[j].y);
+                if (TENSOR) ax[k] = __ldg(f.axis8 + r[j].y);
                 if (r[j].x >= 0) {
                     S1[k] = __ldg(a.S_in + r[j].x);
                     if (MULTIROCK) rk[k] = __ldg(f.rock8 + r[j].x);
@@ -258,16 +285,19 @@ __device__ __forceinline__ double gather_cell(const TabLayout& L, const EuGridDe
             const bool valid = r[j].x != EU_REC_PAD;
             const bool interior = r[j].x >= 0;
             const bool own = !interior || c < r[j].x;
-            const int rk1 = MULTIROCK ? rk[k] : 0;
+            const int axk = TENSOR ? ax[k] : 0;
+            const int rk1 = MULTIROCK ? (TENSOR ? 3*rk[k] + axk : rk[k]) : 0;
+            const int rk0 = TENSOR ? 3*rock0 + axk : rock0;
             double lw1, lo1;
             Mob<ROCKS, MULTIROCK>::both(L, t, rk1, S1[k], lw1, lo1);
             double cap_coef = 0.0, Tdpc = 0.0;
             if (CAP) {
-                cap_coef = cap_coefficient<ROCKS, MULTIROCK>(L, t, rock0, rk1, S0, S1[k]);
+                cap_coef = cap_coefficient<ROCKS, MULTIROCK>(L, t, rk0, rk1, S0, S1[k]);
                 Tdpc = T[k]*(own ? (pc1[k] - pc0) : (pc0 - pc1[k]));
             }
-            const double contrib = face_contribution<CAP>(own, interior, qg[k].x, NN ? qg[k].x*nn[k] : qg[k].x, qg[k].y, lw0, lo0,
-                                                          lw1, lo1, a.method_viscous, a.method_gravity, cap_coef, Tdpc);
+            const double contrib = face_contribution<CAP>(own, interior, qg[k].x, NN ? qg[k].x*nn[k] : qg[k].x, qg[k].y,
+                                                          own0.w(axk), own0.o(axk), lw1, lo1, a.method_viscous, a.method_gravity,
+                                                          cap_coef, Tdpc);
             acc += valid ? contrib : 0.0;
         }
     }
@@ -276,11 +306,11 @@ __device__ __forceinline__ double gather_cell(const TabLayout& L, const EuGridDe
 
 // One face at a time from the SELL records: cells with more than 8 faces (slot_mask = all), and the explicit
 // slots of a slice class (slot_mask = those slots).  Same arithmetic as gather_cell.
-template <bool ROCKS, bool MULTIROCK, bool CAP, bool NN>
+template <bool ROCKS, bool MULTIROCK, bool CAP, bool NN, bool TENSOR>
 __device__ __noinline__ double gather_cell_loop(const TabLayout& L, const EuGridDev& g, const EuTablesDev& t,
                                                 const EuFastDev& f, const EuStepArgs& a, const int2* __restrict__ recp,
                                                 int width, unsigned slot_mask, int c, double S0, int rock0, double pc0,
-                                                double lw0, double lo0)
+                                                const OwnMob<TENSOR>& own0)
 {
     double acc = 0.0;
     for (int j = 0; j < width; ++j) {
@@ -293,26 +323,29 @@ __device__ __noinline__ double gather_cell_loop(const TabLayout& L, const EuGrid
         const double q = qg.x, G = qg.y;
         const double nn = NN ? f.nn[r.y] : 1.0;
         const double S1 = interior ? a.S_in[r.x] : g.bnd_sat[-2 - r.x];
-        const int rk = (MULTIROCK && interior) ? f.rock8[r.x] : rock0;
+        const int axk = TENSOR ? f.axis8[r.y] : 0;
+        int rk = (MULTIROCK && interior) ? f.rock8[r.x] : rock0;
+        int rk0 = rock0;
+        if (TENSOR) { rk = 3*rk + axk; rk0 = 3*rock0 + axk; }
         double lw1, lo1;
         Mob<ROCKS, MULTIROCK>::both(L, t, rk, S1, lw1, lo1);
         double cap_coef = 0.0, Tdpc = 0.0;
         if (CAP && interior) {
-            cap_coef = cap_coefficient<ROCKS, MULTIROCK>(L, t, rock0, rk, S0, S1);
+            cap_coef = cap_coefficient<ROCKS, MULTIROCK>(L, t, rk0, rk, S0, S1);
             const double pc1 = a.pc_in[r.x];
             Tdpc = f.T[r.y]*(own ? (pc1 - pc0) : (pc0 - pc1));
         }
-        acc += face_contribution<CAP>(own, interior, q, q*nn, G, lw0, lo0, lw1, lo1, a.method_viscous, a.method_gravity,
-                                      cap_coef, Tdpc);
+        acc += face_contribution<CAP>(own, interior, q, q*nn, G, own0.w(axk), own0.o(axk), lw1, lo1, a.method_viscous,
+                                      a.method_gravity, cap_coef, Tdpc);
     }
     return acc;
 }
 
 // source term (:293-299), explicit update (EulerUpstream_impl.hpp:371-374), range check / clamp (:336-349) and the
 // capillary pressure of the new state (Residual_impl.hpp:459-467, fused); returns the new saturation
-template <bool ROCKS, bool MULTIROCK, bool CAP>
+template <bool ROCKS, bool MULTIROCK, bool CAP, bool TENSOR>
 __device__ __forceinline__ double finish_cell(const TabLayout& L, const EuTablesDev& t, const EuFastDev& f, const EuStepArgs& a,
-                                              int c, double S0, int rock0, double lw0, double lo0, double inv_pv, double acc,
+                                              int c, double S0, int rock0, const OwnMob<TENSOR>& own0, double inv_pv, double acc,
                                               double& pcn)
 {
     if (a.n_src > 0) {
@@ -320,7 +353,16 @@ __device__ __forceinline__ double finish_cell(const TabLayout& L, const EuTables
         int lo = 0, hi = a.n_src;
         while (lo < hi) { const int mid = (lo + hi) >> 1; if (a.src_cell[mid] < c) lo = mid + 1; else hi = mid; }
         if (lo < a.n_src && a.src_cell[lo] == c) rate = a.src_rate[lo];
-        if (rate < 0.0) rate *= lw0/(lw0 + lo0);
+        if (rate < 0.0) {
+            if (TENSOR) {        // fractionalFlow of the tensor class: mean over the three directions (..AnisotropicRelperm_impl.hpp:57-72)
+                double ff = 0.0;
+#pragma unroll
+                for (int ax = 0; ax < 3; ++ax) ff += own0.w(ax)/(own0.w(ax) + own0.o(ax));
+                rate *= ff/3.0;
+            } else {
+                rate *= own0.w(0)/(own0.w(0) + own0.o(0));
+            }
+        }
         acc += rate;
     }
     if (a.residual_out) a.residual_out[c] = acc;
@@ -339,6 +381,13 @@ __device__ __forceinline__ double finish_cell(const TabLayout& L, const EuTables
     // read their neighbours' mobilities instead of evaluating the rock curves again
     double lwn, lon;
     pcn = 0.0;
+    if (TENSOR) {                // no marches for this class: only the capillary pressure (table 3 r holds the pc column)
+        if (CAP) {
+            pcn = Mob<ROCKS, MULTIROCK>::pc(L, 3*rock0, sat, 1.0);
+            a.pc_out[c] = pcn;
+        }
+        return sat;
+    }
     if (CAP) {
         Mob<ROCKS, MULTIROCK>::both_and_pc(L, t, rock0, sat, ROCKS ? f.pcscale[c] : 1.0, lwn, lon, pcn);
         a.pc_out[c] = pcn;
@@ -481,11 +530,17 @@ __device__ __forceinline__ void march_step(const TabLayout& L, const EuGridDev& 
     }
     if (RECORDS) {                      // boundary / fault faces of this class, from the SELL records
         const int base = f.slice_base[c >> 5];
-        acc += gather_cell_loop<ROCKS, MULTIROCK, CAP, NN>(L, g, t, f, a, f.rec + base + lane, 32 - __clz(cl->rec_mask),
-                                                           (unsigned)cl->rec_mask, c, m.S0, m.rock0, m.pc0, m.lw0, m.lo0);
+        OwnMob<false> own0;
+        own0.lw[0] = m.lw0; own0.lo[0] = m.lo0;
+        acc += gather_cell_loop<ROCKS, MULTIROCK, CAP, NN, false>(L, g, t, f, a, f.rec + base + lane, 32 - __clz(cl->rec_mask),
+                                                                  (unsigned)cl->rec_mask, c, m.S0, m.rock0, m.pc0, own0);
     }
     double pcn;
-    finish_cell<ROCKS, MULTIROCK, CAP>(L, t, f, a, c, m.S0, m.rock0, m.lw0, m.lo0, inv_pv, acc, pcn);
+    {
+        OwnMob<false> own0;
+        own0.lw[0] = m.lw0; own0.lo[0] = m.lo0;
+        finish_cell<ROCKS, MULTIROCK, CAP, false>(L, t, f, a, c, m.S0, m.rock0, own0, inv_pv, acc, pcn);
+    }
     m.S0 = S5; m.lw0 = lam[5].x; m.lo0 = lam[5].y; m.rock0 = rk[5]; m.pc0 = pc1[5];
 }
 
@@ -513,7 +568,7 @@ __device__ __noinline__ void march_item_records(const TabLayout& L, const EuGrid
 
 // One slice through its descriptors / records: slices next to a slab boundary (with the halo push), slices that
 // straddle the own range, irregular slices (faults, cells with other than six faces).
-template <bool ROCKS, bool MULTIROCK, bool CAP, bool NN, int B6, int B8>
+template <bool ROCKS, bool MULTIROCK, bool CAP, bool NN, int B6, int B8, bool TENSOR>
 __device__ __forceinline__ void slice_generic(const TabLayout& L, const EuGridDev& g, const EuTablesDev& t, const EuFastDev& f,
                                               const EuStepArgs& a, const EuHaloDev& halo, int s, int range, int lane,
                                               int slice_lo)
@@ -530,13 +585,12 @@ __device__ __forceinline__ void slice_generic(const TabLayout& L, const EuGridDe
         const int2* __restrict__ recp = f.rec + base + lane;
         const int2* __restrict__ dscp = f.desc + (base >> 5);
         double acc;
-        double lw0, lo0;
-        Mob<ROCKS, MULTIROCK>::both(L, t, rock0, S0, lw0, lo0);
-        if (width <= 6)      acc = gather_cell<ROCKS, MULTIROCK, CAP, NN, 6, B6>(L, g, t, f, a, recp, dscp, width, c, S0, rock0, pc0, lw0, lo0);
-        else if (width <= 8) acc = gather_cell<ROCKS, MULTIROCK, CAP, NN, 8, B8>(L, g, t, f, a, recp, dscp, width, c, S0, rock0, pc0, lw0, lo0);
-        else                 acc = gather_cell_loop<ROCKS, MULTIROCK, CAP, NN>(L, g, t, f, a, recp, width, 0xffffffffu, c, S0, rock0, pc0, lw0, lo0);
+        const OwnMob<TENSOR> own0 = own_mobilities<ROCKS, MULTIROCK, TENSOR>(L, t, rock0, S0);
+        if (width <= 6)      acc = gather_cell<ROCKS, MULTIROCK, CAP, NN, 6, B6, TENSOR>(L, g, t, f, a, recp, dscp, width, c, S0, rock0, pc0, own0);
+        else if (width <= 8) acc = gather_cell<ROCKS, MULTIROCK, CAP, NN, 8, B8, TENSOR>(L, g, t, f, a, recp, dscp, width, c, S0, rock0, pc0, own0);
+        else                 acc = gather_cell_loop<ROCKS, MULTIROCK, CAP, NN, TENSOR>(L, g, t, f, a, recp, width, 0xffffffffu, c, S0, rock0, pc0, own0);
         double pcn;
-        const double sat = finish_cell<ROCKS, MULTIROCK, CAP>(L, t, f, a, c, S0, rock0, lw0, lo0, inv_pv, acc, pcn);
+        const double sat = finish_cell<ROCKS, MULTIROCK, CAP, TENSOR>(L, t, f, a, c, S0, rock0, own0, inv_pv, acc, pcn);
         if (range >= 0) {
             // this cell is a ghost of the neighbour rank: store it into the neighbour's HBM as well
             const int first = (range == 0 ? slice_lo : halo.b_lo)*EU_SLICE;
@@ -564,7 +618,7 @@ __device__ __forceinline__ void slice_generic(const TabLayout& L, const EuGridDe
 
 // Persistent grid.  Processing order: the two slice ranges next to slab boundaries (multi-GPU runs; their results
 // are also pushed into the neighbours' ghost cells), then the work items of the interior, item v to warp v mod #warps.
-template <bool ROCKS, bool MULTIROCK, bool CAP, bool NN, int B6, int B8, int MINB>
+template <bool ROCKS, bool MULTIROCK, bool CAP, bool NN, int B6, int B8, int MINB, bool TENSOR>
 __global__ void __launch_bounds__(kBlock, MINB) k_fast_step(EuGridDev g, EuTablesDev t, EuFastDev f, EuStepArgs a,
                                                             EuHaloDev halo, int slice_lo, int slice_hi, int class_smem_offset)
 {
@@ -604,7 +658,7 @@ __global__ void __launch_bounds__(kBlock, MINB) k_fast_step(EuGridDev g, EuTable
         for (; v < nAB; v += n_warps) {
             const int range = v < nA ? 0 : 1;
             const int s = v < nA ? slice_lo + v : halo.b_lo + (v - nA);
-            slice_generic<ROCKS, MULTIROCK, CAP, NN, B6, B8>(L, g, t, f, a, halo, s, range, lane, slice_lo);
+            slice_generic<ROCKS, MULTIROCK, CAP, NN, B6, B8, TENSOR>(L, g, t, f, a, halo, s, range, lane, slice_lo);
         }
     }
     // ---- interior items
@@ -617,8 +671,8 @@ __global__ void __launch_bounds__(kBlock, MINB) k_fast_step(EuGridDev g, EuTable
         int2 item_next = item;
         if (has_next) item_next = __ldg(f.items + vi + n_warps);
         const int cls = int(unsigned(item.y) >> 16);
-        if (cls == EU_ITEM_GENERIC) {
-            slice_generic<ROCKS, MULTIROCK, CAP, NN, B6, B8>(L, g, t, f, a, halo, item.x, -1, lane, slice_lo);
+        if (TENSOR || cls == EU_ITEM_GENERIC) {       // (no slice classes are built for the tensor class)
+            slice_generic<ROCKS, MULTIROCK, CAP, NN, B6, B8, TENSOR>(L, g, t, f, a, halo, item.x, -1, lane, slice_lo);
         } else {
             const EuSliceClass* cl = classes + cls;
             if (cl->rec_mask != 0) march_item_records<ROCKS, MULTIROCK, CAP, NN>(L, g, t, f, a, cl, item.x, item.y & 0xffff, lane);
@@ -645,7 +699,9 @@ __global__ void __launch_bounds__(kBlock) k_fast_state(EuGridDev g, EuTablesDev 
     }
     for (int c = lo + blockIdx.x*blockDim.x + threadIdx.x; c < hi; c += gridDim.x*blockDim.x) {
         double lw, lo_, pcv;
-        Mob<ROCKS, MULTIROCK>::both_and_pc(L, t, MULTIROCK ? f.rock8[c] : 0, S[c], ROCKS ? f.pcscale[c] : 1.0, lw, lo_, pcv);
+        // (tensor mobility: table 3 r holds the pc column; the pairs are not used by that class)
+        const int table = (MULTIROCK ? f.rock8[c] : 0)*(f.axis8 ? 3 : 1);
+        Mob<ROCKS, MULTIROCK>::both_and_pc(L, t, table, S[c], ROCKS ? f.pcscale[c] : 1.0, lw, lo_, pcv);
         if (pc) pc[c] = pcv;
         lam[c] = make_double2(lw, lo_);
     }
@@ -656,7 +712,7 @@ __global__ void __launch_bounds__(kBlock) k_fast_state(EuGridDev g, EuTablesDev 
 size_t eu_fast_smem_bytes(const EuTablesDev& t)
 {
     if (t.n_rocks == 0) return 0;
-    size_t b = size_t(56)*t.n_nodes_total + 4*(EU_MAX_ROCKS + 2) + size_t(t.n_rocks)*t.n_buckets;
+    size_t b = size_t(56)*t.n_nodes_total + 4*(EU_MAX_TABLES + 2) + size_t(t.n_rocks)*t.n_buckets;
     return (b + 15) & ~size_t(15);
 }
 
@@ -672,13 +728,13 @@ void eu_launch_fast_state(const EuGridDev& g, const EuTablesDev& t, const EuFast
     else                     k_fast_state<false, false><<<blocks, kBlock, 0, st>>>(g, t, f, S, pc, lam, lo, hi);
 }
 
-template <bool ROCKS, bool MULTIROCK, bool CAP, bool NN, int B6, int B8, int MINB>
+template <bool ROCKS, bool MULTIROCK, bool CAP, bool NN, int B6, int B8, int MINB, bool TENSOR = false>
 static void launch_variant(const EuGridDev& g, const EuTablesDev& t, const EuFastDev& f, const EuStepArgs& a,
                            const EuHaloDev& halo, int slice_lo, int slice_hi, int n_sms, size_t smem_tables, cudaStream_t st)
 {
     static int blocks_per_sm = 0;
     static size_t smem_seen = 0;
-    auto kern = k_fast_step<ROCKS, MULTIROCK, CAP, NN, B6, B8, MINB>;
+    auto kern = k_fast_step<ROCKS, MULTIROCK, CAP, NN, B6, B8, MINB, TENSOR>;
     // shared memory: rock tables | slice classes
     const size_t smem = smem_tables + sizeof(EuSliceClass)*EU_MAX_CLASSES;
     if (blocks_per_sm == 0 || smem != smem_seen) {      // (another solver in this process may have larger tables)
@@ -727,6 +783,14 @@ static void launch_fast2(const EuGridDev& g, const EuTablesDev& t, const EuFastD
 {
     const bool cap = a.method_capillary != 0;
     const bool nn = f.nn != nullptr;
+    if (ROCKS && MULTIROCK && f.axis8 != nullptr) {
+        // diagonal tensor mobility: generic gather only, 2 blocks per SM (128 registers)
+        if (cap && nn)   launch_variant<ROCKS, MULTIROCK, true, true, 3, 4, 2, ROCKS && MULTIROCK>(g, t, f, a, halo, slice_lo, slice_hi, n_sms, smem, st);
+        else if (cap)    launch_variant<ROCKS, MULTIROCK, true, false, 3, 4, 2, ROCKS && MULTIROCK>(g, t, f, a, halo, slice_lo, slice_hi, n_sms, smem, st);
+        else if (nn)     launch_variant<ROCKS, MULTIROCK, false, true, 3, 4, 2, ROCKS && MULTIROCK>(g, t, f, a, halo, slice_lo, slice_hi, n_sms, smem, st);
+        else             launch_variant<ROCKS, MULTIROCK, false, false, 3, 4, 2, ROCKS && MULTIROCK>(g, t, f, a, halo, slice_lo, slice_hi, n_sms, smem, st);
+        return;
+    }
     if (cap && nn)       launch_fast<ROCKS, MULTIROCK, true, true>(g, t, f, a, halo, slice_lo, slice_hi, n_sms, smem, st);
     else if (cap)        launch_fast<ROCKS, MULTIROCK, true, false>(g, t, f, a, halo, slice_lo, slice_hi, n_sms, smem, st);
     else if (nn)         launch_fast<ROCKS, MULTIROCK, false, true>(g, t, f, a, halo, slice_lo, slice_hi, n_sms, smem, st);

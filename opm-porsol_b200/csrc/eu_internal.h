@@ -29,7 +29,8 @@
 
 #include "../../include/euler_b200.h"
 
-#define EU_MAX_ROCKS 16
+#define EU_MAX_ROCKS 16          /* rock types the caller may pass */
+#define EU_MAX_TABLES 48         /* curve sets in shared memory: one per rock, or three (x, y, z) for tensor mobility */
 #define EU_SLICE 32
 #define EU_REC_PAD (-1)
 
@@ -122,6 +123,7 @@ struct EuFastDev {
     const double* inv_porevol;   // 1/(volume*poro)
     const double* pcscale;
     const unsigned char* rock8;
+    const unsigned char* axis8;  // per unique face: axis of its (axis-aligned) normal -- FAST tensor mobility only, else NULL
     long long F;
     int prefetch;             // marches request the next cell's lines into L2 one step ahead
 };
@@ -182,6 +184,9 @@ void eu_launch_build_records(const EuGridDev& g, const int* owner_hf, const int*
 void eu_launch_contract(const EuGridDev& g, const EuTablesDev& t, const int* owner_hf, const int* fid_of_hf,
                         const double gravity[3], int method_gravity, double* G, double* T, double* nn,
                         double* nn_maxdev, cudaStream_t st);
+// tensor mobility in FAST mode: are all face normals axis-aligned (flag[0] |= 1 if not)?  axis per unique face
+void eu_launch_axis_check(const EuGridDev& g, int* flag, cudaStream_t st);
+void eu_launch_face_axis(const EuGridDev& g, const int* owner_hf, const int* fid_of_hf, unsigned char* axis8, cudaStream_t st);
 void eu_launch_pcscale(const EuGridDev& g, const EuTablesDev& t, double* pcscale, unsigned char* rock8, double* inv_porevol, cudaStream_t st);
 // CFL terms (CflCalculator.hpp); results are block minima reduced to out[0]
 void eu_launch_cfl_velocity_compact(const EuGridDev& g, double cfl_factor, const double* hf_flux, const int* fid_of_hf,

@@ -340,6 +340,33 @@ __global__ void k_contract(EuGridDev g, EuTablesDev t, const int* __restrict__ o
     if (maxdev > 0.0) atomicMax(nn_maxdev_bits, (unsigned long long)__double_as_longlong(maxdev));
 }
 
+// FAST mode with diagonal tensor mobility needs axis-aligned face normals (eu_fast.cu): exactly one component
+// of magnitude > 1e-14.
+__device__ __forceinline__ int normal_axis(const double* __restrict__ n, bool* aligned)
+{
+    const double a0 = fabs(n[0]), a1 = fabs(n[1]), a2 = fabs(n[2]);
+    const int ax = (a0 >= a1 && a0 >= a2) ? 0 : (a1 >= a2 ? 1 : 2);
+    const double minor = (ax == 0) ? fmax(a1, a2) : (ax == 1 ? fmax(a0, a2) : fmax(a0, a1));
+    *aligned = minor <= 1e-14;
+    return ax;
+}
+__global__ void k_axis_check(EuGridDev g, int* __restrict__ flag)
+{
+    const long long h = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+    if (h >= g.H) return;
+    bool aligned;
+    normal_axis(g.hf_normal + 3*h, &aligned);
+    if (!aligned) atomicOr(flag, 1);
+}
+__global__ void k_face_axis(EuGridDev g, const int* __restrict__ owner_hf, const int* __restrict__ fid_of_hf,
+                            unsigned char* __restrict__ axis8)
+{
+    const long long h = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+    if (h >= g.H || owner_hf[h] != h) return;
+    bool aligned;
+    axis8[fid_of_hf[h]] = (unsigned char)normal_axis(g.hf_normal + 3*h, &aligned);
+}
+
 __global__ void k_pcscale(EuGridDev g, EuTablesDev t, double* __restrict__ pcscale, unsigned char* __restrict__ rock8,
                           double* __restrict__ inv_porevol)
 {
@@ -764,6 +791,14 @@ void eu_launch_contract(const EuGridDev& g, const EuTablesDev& t, const int* own
     cudaMemsetAsync(nn_maxdev, 0, sizeof(double), st);
     k_contract<<<div_up(g.n_local, kThreads), kThreads, 0, st>>>(g, t, owner_hf, fid_of_hf, gravity[0], gravity[1], gravity[2],
                                                                  method_gravity, G, T, nn, (unsigned long long*)nn_maxdev);
+}
+void eu_launch_axis_check(const EuGridDev& g, int* flag, cudaStream_t st)
+{
+    if (g.H > 0) k_axis_check<<<div_up(g.H, kThreads), kThreads, 0, st>>>(g, flag);
+}
+void eu_launch_face_axis(const EuGridDev& g, const int* owner_hf, const int* fid_of_hf, unsigned char* axis8, cudaStream_t st)
+{
+    if (g.H > 0) k_face_axis<<<div_up(g.H, kThreads), kThreads, 0, st>>>(g, owner_hf, fid_of_hf, axis8);
 }
 void eu_launch_pcscale(const EuGridDev& g, const EuTablesDev& t, double* pcscale, unsigned char* rock8, double* inv_porevol,
                        cudaStream_t st)

@@ -2,7 +2,7 @@
 //
 // Same class template and public members as the reference (opm/porsol/euler/EulerUpstreamResidual.hpp:57-125,
 // _impl.hpp:375-505); the residual is computed on a B200 through eu_compute_residual of include/euler_b200.h.
-// The reference uses the class in two places: as a member of EulerUpstream (EulerUpstream.hpp:144) and in
+// The reference uses the class in two places: as a member of EulerUpstream (EulerUpstream.hpp:126-128) and in
 // ImplicitCapillarity::transportSolve, which calls computeResidual with method_capillary = false and negates
 // the result into injection rates for its capillary pressure solve (ImplicitCapillarity_impl.hpp:176-183).
 //

@@ -109,6 +109,7 @@ def load_library():
     L.eu_set_fluid.argtypes = [C.c_void_p, C.POINTER(_Fluid)]
     L.eu_grid_end.argtypes = [C.c_void_p]
     L.eu_local_cells.argtypes = [C.c_void_p]
+    L.eu_resolved_mode.argtypes = [C.c_void_p]
     L.eu_local_halffaces.argtypes = [C.c_void_p]
     L.eu_local_halffaces.restype = C.c_longlong
     L.eu_regular_fraction.argtypes = [C.c_void_p]
@@ -370,6 +371,10 @@ class EulerUpstream:
         if rc != EU_OK and raise_on_error:
             raise EulerB200Error(rc, self.L.eu_last_error(self.h).decode())
         return self.last_report
+
+    def resolved_mode(self):
+        """'strict' or 'fast': what EU_MODE_AUTO resolved to for this grid and property class."""
+        return {1: "strict", 2: "fast"}.get(int(self.L.eu_resolved_mode(self.h)), "auto")
 
     def regular_fraction(self):
         return float(self.L.eu_regular_fraction(self.h))

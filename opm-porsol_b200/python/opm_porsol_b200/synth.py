@@ -422,6 +422,20 @@ def config_c2(n=100, seed=7):
                      hf_flux=constant_velocity_flux(g, (1e-6, 5e-7, 2.5e-7)), time=86400.0)
 
 
+def config_c2b(n=100, seed=7):
+    """SURVEY 8d variant C2b: the C2 grid with the property class aniso_simulator_test really uses,
+    ReservoirPropertyCapillaryAnisotropicRelperm (diagonal tensor mobility): krxx != kryy != krzz tables, pc table
+    without J-scaling (RockAnisotropicRelperm.hpp:57-62,79-83)."""
+    c = config_c2(n, seed)
+    t = c.rocks[0]
+    f = np.array([1.0, 0.7, 0.4])
+    c.rocks = [RockTable(s=t.s, pc=_f64(t.J*2.0e4), kr_w=_f64(t.krw[:, None]*f[None, :]), kr_o=_f64(t.kro[:, None]*f[None, ::-1]))]
+    c.mobility_kind = 1
+    c.use_j = False
+    c.name = "C2b"
+    return c
+
+
 def lognormal_perm(N, seed, mean_md=100.0, sigma=1.0, kz_ratio=0.1):
     z = box_muller(seed, N)
     kx = np.exp(np.log(mean_md*MILLIDARCY) + sigma*z)
@@ -459,15 +473,17 @@ def config_c4(nx=512, ny=512, nz=256, seed=44, capillary=False):
 
 
 def random_geometry_case(nx, ny, nz, seed=1, periodic=(False, False, False), n_rocks=0, full_tensor=True,
-                         sources=True, mobility_kind=0, use_j=True):
+                         sources=True, mobility_kind=0, use_j=True, perturb_normals=True):
     """Stress case: Cartesian topology with randomised (but pairwise consistent) face normals,
     areas and centroids, random full-tensor K, random porosity and saturations, oblique flux.
     The transport scheme never checks geometric consistency, so this exercises every term
-    of the face flux with generic operands (oblique normals, off-diagonal K)."""
+    of the face flux with generic operands (oblique normals, off-diagonal K).
+    ``perturb_normals=False`` keeps the axis-aligned normals of the Cartesian grid (everything else stays
+    random): the geometry class on which FAST mode covers the diagonal tensor mobility."""
     g = cartesian_grid(nx, ny, nz, 1.0, 0.8, 0.5, unique_bids=True, periodic=periodic)
     N, H = g["N"], g["hf_nbr"].shape[0]
     rs = np.random.Generator(np.random.MT19937(seed))
-    normal = g["hf_normal"] + 0.3*(rs.random((H, 3)) - 0.5)
+    normal = g["hf_normal"] + 0.3*(rs.random((H, 3)) - 0.5)*(1.0 if perturb_normals else 0.0)
     normal /= np.sqrt((normal**2).sum(axis=1))[:, None]
     area = g["hf_area"]*(0.7 + 0.6*rs.random(H))
     cent = g["hf_centroid"] + 0.05*(rs.random((H, 3)) - 0.5)

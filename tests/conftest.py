@@ -56,6 +56,20 @@ def tensor_cases():
     return [("tensor_2rocks_periodic", c), ("tensor_norock", d)]
 
 
+def tensor_aligned_cases():
+    """Diagonal tensor mobility (ReservoirPropertyCapillaryAnisotropicRelperm, the class aniso_simulator_test uses) on
+    grids with axis-aligned face normals: FAST mode applies (kernels)."""
+    from opm_porsol_b200 import synth
+    a = synth.random_geometry_case(6, 5, 4, seed=15, n_rocks=2, periodic=(True, False, False), mobility_kind=1,
+                                   perturb_normals=False)
+    b = synth.random_geometry_case(5, 7, 3, seed=16, n_rocks=3, mobility_kind=1, perturb_normals=False)
+    b.method_gravity = False
+    c = synth.random_geometry_case(9, 4, 4, seed=17, n_rocks=1, periodic=(False, True, True), mobility_kind=1,
+                                   perturb_normals=False, sources=False)
+    c.method_capillary = False
+    return [("tensor_aligned_2rocks_periodic", a), ("tensor_aligned_3rocks_nogravity", b), ("tensor_aligned_1rock_nocap", c)]
+
+
 def active_cfl_dt(case, cfl):
     """courant * min over the CFL terms the solver actually uses (EulerUpstream_impl.hpp:275-318)."""
     v = cfl[0] if (case.method_viscous and case.use_cfl_viscous) else 1e99

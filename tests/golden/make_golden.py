@@ -6,8 +6,9 @@
 
 Each fixture stores the seeded inputs' identity (case name + generator arguments are in
 tests/conftest.py: small_cases / tensor_cases) and the reference's outputs: CFL factors, the three CFL
-times, saturation and residual after each of 3 substeps, and a full transportSolve (saturation,
-step count, attempts).  The GPU box has no /root/reference; tests compare against these files there.
+times, saturation and residual after each of 3 substeps, a full transportSolve (saturation,
+step count, attempts), computeResidual with explicit method flags and the SimulatorUtilities.hpp diagnostics
+(cell velocity, phase velocities, capillary pressures).  The GPU box has no /root/reference; tests compare against these files there.
 """
 import os
 import sys
@@ -41,6 +42,12 @@ def main():
             step_res.append(o["residual"].copy())
         out = dict(cfl_factors=fac, cfl_times=cfl, dt=dt, step_sat=np.array(step_sat), step_res=np.array(step_res),
                    input_checksum=np.array([case.sat0.sum(), case.hf_flux.sum(), case.perm.sum(), case.hf_area.sum()]))
+        # the residual as an operator (ImplicitCapillarity's call: capillary off) and the post-transport diagnostics
+        out.update(res_vg=ref.compute_residual(case.sat0, (True, True, False)),
+                   res_gc=ref.compute_residual(case.sat0, (False, True, True)),
+                   cell_velocity=ref.cell_velocity(), cap_pressures=ref.cap_pressures(case.sat0))
+        vw, vo = ref.phase_velocities(case.sat0, out["cell_velocity"])
+        out.update(water_velocity=vw, oil_velocity=vo)
         if case.mobility_kind == 0:
             time = 17.3*total
             sol = ref.transport_solve(case.sat0, time=time)

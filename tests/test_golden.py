@@ -31,6 +31,12 @@ def test_oracle_reproduces_golden(name, case):
         s = o["sat"]
         assert np.array_equal(o["residual"], g["step_res"][q])
         assert np.array_equal(s, g["step_sat"][q])
+    assert np.array_equal(port.compute_residual(case.sat0, (True, True, False)), g["res_vg"])
+    assert np.array_equal(port.compute_residual(case.sat0, (False, True, True)), g["res_gc"])
+    assert np.array_equal(port.cell_velocity(), g["cell_velocity"])
+    assert np.array_equal(port.cap_pressures(case.sat0), g["cap_pressures"])
+    vw, vo = port.phase_velocities(case.sat0, g["cell_velocity"])
+    assert np.array_equal(vw, g["water_velocity"]) and np.array_equal(vo, g["oil_velocity"])
     if case.mobility_kind == 0:
         sol = port.transport_solve(case.sat0, time=float(g["solve_time"]))
         assert sol["nsteps"] == int(g["solve_nsteps"]) and sol["attempts"] == int(g["solve_attempts"])
@@ -61,6 +67,17 @@ def test_cuda_reproduces_golden(name, case, mode):
         else:
             assert np.abs(s - g["step_sat"][q]).max() <= 1e-12
         dev.upload_saturation(g["step_sat"][q])
+    # operator entry points against the reference's own outputs
+    for key, m in (("res_vg", (True, True, False)), ("res_gc", (False, True, True))):
+        r = dev.computeResidual(case.sat0, case.gravity, None, inj, *m)
+        if mode == "strict":
+            assert np.array_equal(r, g[key])
+        else:
+            assert np.abs(r - g[key]).max() <= 1e-12*(np.abs(g[key]).max() + 1e-300)
+    assert np.array_equal(dev.cellVelocity(), g["cell_velocity"])
+    assert np.array_equal(dev.computeCapPressures(case.sat0), g["cap_pressures"])
+    vw, vo = dev.phaseVelocities(case.sat0, g["cell_velocity"])
+    assert np.array_equal(vw, g["water_velocity"]) and np.array_equal(vo, g["oil_velocity"])
     if case.mobility_kind == 0:
         sat = case.sat0.copy()
         rep = dev.transportSolve(sat, float(g["solve_time"]), case.gravity, case.hf_flux, inj)

@@ -7,12 +7,12 @@ order (STRICT residual, every diagnostic in every mode); FAST residual within 1e
 import numpy as np
 import pytest
 
-from conftest import small_cases, tensor_cases
+from conftest import small_cases, tensor_aligned_cases, tensor_cases
 
 pytestmark = pytest.mark.gpu
 
 METHOD_SETS = [(True, True, False), (True, False, False), (False, True, True), (True, True, True)]
-ALL = small_cases() + tensor_cases()
+ALL = small_cases() + tensor_cases() + tensor_aligned_cases()
 
 
 def _solvers(case, mode):
@@ -37,10 +37,10 @@ def _solvers(case, mode):
 @pytest.mark.parametrize("name,case", ALL, ids=[n for n, _ in ALL])
 def test_compute_residual_operator(name, case, mode):
     if case.mobility_kind == 1 and mode == "fast":
-        mode = "auto"                                   # tensor mobility runs the STRICT kernels
+        mode = "auto"                                   # tensor mobility: FAST only on axis-aligned grids
     dev, port = _solvers(case, mode)
     inj = (case.src_cell, case.src_rate)
-    exact = mode != "fast"
+    exact = mode == "strict"
     rng = np.random.default_rng(5)
     sat_b = np.clip(case.sat0 + 0.05*rng.standard_normal(case.N), 0.02, 0.98)
     dev.upload_state(case.sat0, case.hf_flux)           # a resident state the operator must leave alone

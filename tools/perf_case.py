@@ -2,6 +2,7 @@
 """Time one of the BASELINE parity configurations on a B200 (not the bench line: bench.py is).
 
     python tools/perf_case.py c2 --n 160          # n^3 Cartesian, rotated anisotropic K, rock table, V+G+C
+    python tools/perf_case.py c2b --n 160         # the same with diagonal tensor mobility (aniso_simulator_test's class)
     python tools/perf_case.py c3 --dims 256 256 128   # faulted corner-point, lognormal K, 3 rocks, V+G+C
 
 Prints cell-substeps/s of the resident transportSolve with a fixed number of substeps, the algorithmic-byte
@@ -20,7 +21,7 @@ import numpy as np  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("case", choices=["c2", "c3"])
+    ap.add_argument("case", choices=["c2", "c2b", "c3"])
     ap.add_argument("--n", type=int, default=160)
     ap.add_argument("--dims", type=int, nargs=3, default=[256, 256, 128])
     ap.add_argument("--substeps", type=int, default=50)
@@ -32,10 +33,17 @@ def main():
     from opm_porsol_b200 import synth
     from opm_porsol_b200.binding import make_fluid, params_from_case
     t0 = time.time()
-    case = synth.config_c2(a.n) if a.case == "c2" else synth.config_c3(*a.dims)
+    if a.case == "c2b":
+        # tensor mobility: the CFL factors of the scalar twin stand in for the reference's (the step count is fixed here)
+        twin = synth.config_c2(8)
+        fluid, _ = make_fluid(twin)
+        fac = np.array(fluid.cfl_factor[:])
+        case = synth.config_c2b(a.n)
+    else:
+        case = synth.config_c2(a.n) if a.case == "c2" else synth.config_c3(*a.dims)
+        fluid, _ = make_fluid(case)
+        fac = np.array(fluid.cfl_factor[:])
     case.min_steps = case.max_steps = a.substeps
-    fluid, _ = make_fluid(case)
-    fac = np.array(fluid.cfl_factor[:])
     dev = eub.EulerUpstream(device=0, mode="fast")
     dev.init(params_from_case(case))
     dev.initObj(case, cfl_factors=fac)
@@ -63,7 +71,8 @@ def main():
     out = {"case": case.name, "cells": N, "half_faces": H, "faces": n_faces, "kernel_ms": kernel_ms,
            "cell_substeps_per_s": N/(kernel_ms*1e-3), "bytes_per_cell_substep_model": abytes/N,
            "achieved_GBs": abytes/(kernel_ms*1e-3)/1e9, "frac_of_measured_peak": abytes/(kernel_ms*1e-3)/1e9/peak,
-           "regular_slot_fraction": dev.regular_fraction(), "cfl_times": list(cfl), "setup_s": round(setup, 1)}
+           "regular_slot_fraction": dev.regular_fraction(), "cfl_times": list(cfl), "setup_s": round(setup, 1),
+           "mode": dev.resolved_mode()}
     sat = dev.download_saturation()
     out["sat_range"] = [float(sat.min()), float(sat.max())]
     if a.check_strict:
