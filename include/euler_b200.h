@@ -186,6 +186,20 @@ int eu_transport_solve(eu_handle h, double* saturation, double time, const doubl
                        const double* hf_flux, int n_src, const int* src_cell, const double* src_rate,
                        eu_report* report);
 
+/* ---- flux hand-off from the host pressure solver (FlowSolution::outflux, IncompFlowSolverHybrid.hpp:426-438) -----
+ * eu_transport_solve copies `saturation` and `hf_flux` over PCIe inside the call; from pageable memory that copy runs
+ * at a fraction of the link rate.  Two remedies, both optional:
+ *  - eu_host_alloc / eu_host_free: page-locked host memory for the caller's flat flux array (the drop-in C++ header
+ *    gathers pressure_sol.outflux(f) into such a buffer);
+ *  - buffers of >= 1 MiB passed to eu_transport_solve / eu_upload_state / eu_upload_saturation / eu_download_saturation /
+ *    eu_compute_residual that are not page-locked yet are registered with the driver on first use and stay registered
+ *    while the same (pointer, size) keeps coming (an IMPES loop passes the same vectors every step); at most 4
+ *    registrations per solver, released by eu_destroy or eu_host_unpin_all.  Set EU_PIN_CACHE=0 to turn this off
+ *    (e.g. when the application frees and reallocates its vectors between calls). */
+void* eu_host_alloc(unsigned long long bytes);
+void eu_host_free(void* p);
+void eu_host_unpin_all(eu_handle h);
+
 /* ---- device-resident variant: state stays in HBM between calls ------------------------- */
 int eu_upload_state(eu_handle h, const double* saturation, const double* hf_flux);
 int eu_upload_saturation(eu_handle h, const double* saturation);

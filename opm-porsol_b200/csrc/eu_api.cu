@@ -115,6 +115,11 @@ struct eu_solver {
     // ---- state
     DevBuf<double> d_S[2], d_pc[2], d_S_init, d_hf_flux, d_residual, d_block_min, d_scalars;
     DevBuf<double> d_diag;             // scratch of the diagnostics (eu_diag.cu), allocated on first use
+    // host buffers of the caller registered (page-locked) on first use, see include/euler_b200.h
+    struct Pinned { const void* p; size_t bytes; unsigned long long stamp; };
+    std::vector<Pinned> pinned;
+    unsigned long long pin_clock = 0;
+    bool pin_cache = true;
     DevBuf<unsigned long long> d_fail_key;
     DevBuf<int> d_src_cell;
     DevBuf<double> d_src_rate;
@@ -209,6 +214,46 @@ int fail(eu_handle h, int code, const std::string& msg)
             return fail(h, EU_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
         }                                                                                      \
     } while (0)
+
+// Page-lock a caller buffer that keeps coming back (include/euler_b200.h, "flux hand-off").  Best effort: any
+// failure leaves the buffer pageable and the copy correct.
+void unpin_all(eu_handle h)
+{
+    for (const eu_solver::Pinned& e : h->pinned) cudaHostUnregister(const_cast<void*>(e.p));
+    h->pinned.clear();
+    cudaGetLastError();
+}
+
+void pin_host(eu_handle h, const void* p, size_t bytes)
+{
+    if (!h->pin_cache || !p || bytes < (size_t(1) << 20)) return;
+    for (eu_solver::Pinned& e : h->pinned) {
+        if (e.p == p && e.bytes >= bytes) { e.stamp = ++h->pin_clock; return; }
+    }
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type != cudaMemoryTypeUnregistered) return;   // pinned already
+    cudaGetLastError();
+    // a stale registration that overlaps this buffer (the application reallocated its vector) must go first
+    for (size_t i = 0; i < h->pinned.size();) {
+        const char* a = static_cast<const char*>(h->pinned[i].p);
+        const char* b = static_cast<const char*>(p);
+        if (a < b + bytes && b < a + h->pinned[i].bytes) {
+            cudaHostUnregister(const_cast<void*>(h->pinned[i].p));
+            h->pinned.erase(h->pinned.begin() + long(i));
+        } else {
+            ++i;
+        }
+    }
+    if (h->pinned.size() >= 4) {
+        size_t oldest = 0;
+        for (size_t i = 1; i < h->pinned.size(); ++i) if (h->pinned[i].stamp < h->pinned[oldest].stamp) oldest = i;
+        cudaHostUnregister(const_cast<void*>(h->pinned[oldest].p));
+        h->pinned.erase(h->pinned.begin() + long(oldest));
+    }
+    if (cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterPortable) == cudaSuccess)
+        h->pinned.push_back(eu_solver::Pinned{ p, bytes, ++h->pin_clock });
+    cudaGetLastError();
+}
 
 template <class T>
 int upload(eu_handle h, DevBuf<T>& dst, size_t offset, const T* src, size_t count)
@@ -670,6 +715,7 @@ int eu_create(const eu_config* cfg, eu_handle* out)
     h->mode = EU_MODE_STRICT;
     h->n_sms = prop.multiProcessorCount;
     { const char* e = getenv("EU_PREFETCH"); if (e) h->prefetch = atoi(e) != 0; }
+    { const char* e = getenv("EU_PIN_CACHE"); if (e) h->pin_cache = atoi(e) != 0; }
     std::memset(&h->fluid, 0, sizeof(h->fluid));
     std::memset(&h->tab, 0, sizeof(h->tab));
     if ((e = cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking)) != cudaSuccess ||
@@ -686,6 +732,7 @@ void eu_destroy(eu_handle h)
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     cudaStreamSynchronize(h->st);
+    unpin_all(h);
     for (eu_solver::Peer* p : h->peers) {
         for (void* o : p->opened) if (o) cudaIpcCloseMemHandle(o);
         delete p;
@@ -1091,6 +1138,7 @@ int eu_upload_saturation(eu_handle h, const double* saturation)
     if (!h || !saturation) return EU_ERR_ARG;
     if (!h->grid_ready) return fail(h, EU_ERR_ARG, "grid not ready");
     EU_CUDA(h, cudaSetDevice(h->cfg.device));
+    pin_host(h, saturation, size_t(h->n_local)*sizeof(double));
     EU_CUDA(h, cudaMemcpyAsync(h->d_S[h->cur].p, saturation, size_t(h->n_local)*sizeof(double), cudaMemcpyHostToDevice, h->st));
     EU_CUDA(h, cudaStreamSynchronize(h->st));
     return EU_OK;
@@ -1102,6 +1150,8 @@ int eu_upload_state(eu_handle h, const double* saturation, const double* hf_flux
     if (!h->grid_ready) return fail(h, EU_ERR_ARG, "grid not ready");
     EU_CUDA(h, cudaSetDevice(h->cfg.device));
     h->cur = 0;                                  // every rank keeps the same buffer parity
+    pin_host(h, hf_flux, size_t(h->H)*sizeof(double));
+    if (saturation) pin_host(h, saturation, size_t(h->n_local)*sizeof(double));
     EU_CUDA(h, cudaMemcpyAsync(h->d_hf_flux.p, hf_flux, size_t(h->H)*sizeof(double), cudaMemcpyHostToDevice, h->st));
     if (saturation)
         EU_CUDA(h, cudaMemcpyAsync(h->d_S[h->cur].p, saturation, size_t(h->n_local)*sizeof(double), cudaMemcpyHostToDevice, h->st));
@@ -1115,6 +1165,7 @@ int eu_download_saturation(eu_handle h, double* saturation)
     if (!h || !saturation) return EU_ERR_ARG;
     if (!h->grid_ready) return fail(h, EU_ERR_ARG, "grid not ready");
     EU_CUDA(h, cudaSetDevice(h->cfg.device));
+    pin_host(h, saturation, size_t(h->n_local)*sizeof(double));
     EU_CUDA(h, cudaMemcpyAsync(saturation, h->d_S[h->cur].p, size_t(h->n_local)*sizeof(double), cudaMemcpyDeviceToHost, h->st));
     EU_CUDA(h, cudaStreamSynchronize(h->st));
     return EU_OK;
@@ -1189,6 +1240,8 @@ int eu_compute_residual(eu_handle h, const double* saturation, const double grav
     EU_CUDA(h, cudaSetDevice(h->cfg.device));
     const size_t nbytes = size_t(h->n_local)*sizeof(double);
     const int in = h->cur ^ 1;                   // the buffer that does not hold the resident state
+    pin_host(h, saturation, nbytes);
+    if (hf_flux) pin_host(h, hf_flux, size_t(h->H)*sizeof(double));
     // The resident state is parked in d_S_init while both ping-pong buffers serve as scratch.
     EU_CUDA(h, cudaMemcpyAsync(h->d_S_init.p, h->d_S[h->cur].p, nbytes, cudaMemcpyDeviceToDevice, h->st));
     EU_CUDA(h, cudaMemcpyAsync(h->d_S[in].p, saturation, nbytes, cudaMemcpyHostToDevice, h->st));
@@ -1470,6 +1523,15 @@ int eu_transport_solve(eu_handle h, double* saturation, double time, const doubl
     int rc2 = eu_download_saturation(h, saturation);
     return rc != EU_OK ? rc : rc2;
 }
+
+void* eu_host_alloc(unsigned long long bytes)
+{
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, size_t(bytes ? bytes : 1), cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void eu_host_free(void* p) { if (p) cudaFreeHost(p); }
+void eu_host_unpin_all(eu_handle h) { if (h) { cudaSetDevice(h->cfg.device); cudaStreamSynchronize(h->st); unpin_all(h); } }
 
 struct EuBlobHeader {
     int magic, rank, world, own_begin, own_end, n_ghost;

@@ -592,25 +592,13 @@ __device__ __forceinline__ void slice_generic(const TabLayout& L, const EuGridDe
         double pcn;
         const double sat = finish_cell<ROCKS, MULTIROCK, CAP, TENSOR>(L, t, f, a, c, S0, rock0, own0, inv_pv, acc, pcn);
         if (range >= 0) {
-            // this cell is a ghost of the neighbour rank: store it into the neighbour's HBM as well
+            // this cell is a ghost of the neighbour rank: store it into the neighbour's HBM as well (made visible by the
+            // one system fence the warp issues after its last boundary slice, see k_fast_step)
             const int first = (range == 0 ? slice_lo : halo.b_lo)*EU_SLICE;
             const int d = halo.dst[range][c - first];
             if (d >= 0) {
                 halo.peer_S[range][d] = sat;
                 if (CAP && halo.peer_pc[range]) halo.peer_pc[range][d] = pcn;
-            }
-            __threadfence_system();
-        }
-    }
-    if (range >= 0) {
-        __syncwarp();
-        if (lane == 0) {
-            const unsigned done = atomicAdd(halo.counter[range], 1u);
-            if (done == halo.total[range] - 1u) {
-                *halo.counter[range] = 0u;
-                __threadfence_system();
-                *(volatile unsigned*)halo.peer_flag[range] = halo.epoch;
-                __threadfence_system();
             }
         }
     }
@@ -655,10 +643,29 @@ __global__ void __launch_bounds__(kBlock, MINB) k_fast_step(EuGridDev g, EuTable
             __threadfence_system();
         }
         __syncwarp();
+        unsigned done[2] = { 0u, 0u };
         for (; v < nAB; v += n_warps) {
             const int range = v < nA ? 0 : 1;
             const int s = v < nA ? slice_lo + v : halo.b_lo + (v - nA);
             slice_generic<ROCKS, MULTIROCK, CAP, NN, B6, B8, TENSOR>(L, g, t, f, a, halo, s, range, lane, slice_lo);
+            ++done[range];
+        }
+        // One system-scope fence per warp for all its pushes, then the finished-slice counters; the warp that completes
+        // a neighbour's share publishes the epoch in that neighbour's flag word.
+        __threadfence_system();
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                if (done[r] == 0u) continue;
+                const unsigned before = atomicAdd(halo.counter[r], done[r]);
+                if (before + done[r] == halo.total[r]) {
+                    *halo.counter[r] = 0u;
+                    __threadfence_system();
+                    *(volatile unsigned*)halo.peer_flag[r] = halo.epoch;
+                    __threadfence_system();
+                }
+            }
         }
     }
     // ---- interior items

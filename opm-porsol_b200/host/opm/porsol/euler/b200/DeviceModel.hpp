@@ -15,8 +15,10 @@
 #include <euler_b200.h>
 
 #include <algorithm>
+#include <cstddef>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <type_traits>
 #include <utility>
 #include <vector>
@@ -36,6 +38,39 @@ namespace b200 {
             static const bool value = decltype(test<PS>(0))::value;
         };
     }
+
+    /// Flat array of half-face fluxes in page-locked host memory (eu_host_alloc), so that the copy to the device inside
+    /// eu_transport_solve runs at the PCIe rate; falls back to pageable memory if the allocation is refused.
+    class FluxBuffer
+    {
+    public:
+        FluxBuffer() : p_(0), n_(0), pinned_(false) {}
+        ~FluxBuffer() { release(); }
+        FluxBuffer(const FluxBuffer&) = delete;
+        FluxBuffer& operator=(const FluxBuffer&) = delete;
+        void assign(std::size_t n)
+        {
+            release();
+            p_ = static_cast<double*>(eu_host_alloc(static_cast<unsigned long long>(n)*sizeof(double)));
+            pinned_ = p_ != 0;
+            if (!p_) p_ = new double[n ? n : 1];
+            n_ = n;
+            std::fill(p_, p_ + n_, 0.0);
+        }
+        double* data() { return p_; }
+        const double* data() const { return p_; }
+        std::size_t size() const { return n_; }
+        double& operator[](std::size_t i) { return p_[i]; }
+    private:
+        void release()
+        {
+            if (p_) { if (pinned_) eu_host_free(p_); else delete[] p_; }
+            p_ = 0; n_ = 0; pinned_ = false;
+        }
+        double* p_;
+        std::size_t n_;
+        bool pinned_;
+    };
 
     template <class GridInterface, class ReservoirProperties, class BoundaryConditions>
     class DeviceModel
@@ -58,7 +93,7 @@ namespace b200 {
         const ReservoirProperties& reservoirProperties() const { return *prp_; }
         const BoundaryConditions& boundaryConditions() const { return *pbc_; }
         /// pressure_sol.outflux of every half-face, in upload order (filled by gatherFluxes)
-        const std::vector<double>& fluxes() const { return hf_flux_; }
+        const FluxBuffer& fluxes() const { return hf_flux_; }
 
         void check(int rc, const char* who) const
         {
@@ -134,7 +169,7 @@ namespace b200 {
                     }
                 }
             }
-            hf_flux_.assign(size_t(H), 0.0);
+            hf_flux_.assign(size_t(H));
             check(eu_grid_begin(handle_, num_cells_, num_cells_, H));
             // fluid: viscosities, densities, CFL factors, rock tables
             FluidDescription fd;
@@ -206,11 +241,23 @@ namespace b200 {
             check(eu_grid_end(handle_));
         }
 
+        // flat accessor: a const read per half-face, spread over the host cores for large grids
         template <class PressureSolution>
         void gatherFluxes(const PressureSolution& ps, std::true_type)
         {
             const int H = int(hf_flux_.size());
-            for (int hf = 0; hf < H; ++hf) hf_flux_[hf] = detail::flatOutflux(ps, hf, 0);
+            double* out = hf_flux_.data();
+            unsigned nt = H >= (1 << 20) ? std::min(std::thread::hardware_concurrency(), 32u) : 1u;
+            if (nt <= 1) {
+                for (int hf = 0; hf < H; ++hf) out[hf] = detail::flatOutflux(ps, hf, 0);
+                return;
+            }
+            std::vector<std::thread> pool;
+            for (unsigned t = 0; t < nt; ++t) {
+                const int lo = int((long long)H*t/nt), hi = int((long long)H*(t + 1)/nt);
+                pool.emplace_back([&ps, out, lo, hi]() { for (int hf = lo; hf < hi; ++hf) out[hf] = detail::flatOutflux(ps, hf, 0); });
+            }
+            for (std::thread& th : pool) th.join();
         }
         template <class PressureSolution>
         void gatherFluxes(const PressureSolution& ps, std::false_type)
@@ -227,7 +274,7 @@ namespace b200 {
         eu_handle handle_;
         int num_cells_;
         std::string who_;
-        std::vector<double> hf_flux_;
+        FluxBuffer hf_flux_;
     };
 
 } // namespace b200
