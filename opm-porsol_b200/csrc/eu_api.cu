@@ -89,8 +89,9 @@ struct eu_solver {
     // axis-aligned face normals); tabf is `tab` with the set count / offsets of the FAST tables
     EuTablesDev tabf;
     DevBuf<int> d_tab_offset_fast;
-    bool tensor_fast = false;
+    int tensor_fast = 0;               // 0: scalar class; 1: tensor class, axis-aligned normals; 2: tensor class, general normals
     DevBuf<unsigned char> d_axis8;
+    DevBuf<double> d_fv;               // tensor_fast == 2: per-face axis vectors (k_contract_t3), 9 x (F + 1)
     // ---- derived
     DevBuf<int> d_owner_hf, d_fid_of_hf, d_slice_base, d_flags;
     DevBuf<int2> d_strict_list, d_rec, d_desc;
@@ -179,7 +180,9 @@ struct eu_solver {
         f.classes = d_classes.p; f.n_classes = n_classes; f.slice_base = d_slice_base.p; f.rec = d_rec.p; f.desc = d_desc.p;
         f.qg = d_qg.p; f.T = d_T.p; f.nn = use_nn ? d_nn.p : nullptr;
         f.inv_porevol = d_inv_porevol.p; f.pcscale = d_pcscale.p; f.rock8 = d_rock8.p; f.F = F;
-        f.axis8 = tensor_fast ? d_axis8.p : nullptr;
+        f.axis8 = tensor_fast == 1 ? d_axis8.p : nullptr;
+        f.fv = tensor_fast == 2 ? d_fv.p : nullptr;
+        f.fv_stride = (long long)(d_fv.n/9);
         f.prefetch = prefetch;
         return f;
     }
@@ -331,6 +334,8 @@ int ensure_contracted(eu_handle h, const double gravity[3])
                            h->d_scalars.p + 8, h->st);
         EU_CUDA(h, cudaStreamSynchronize(h->st));
     }
+    if (h->tensor_fast == 2)
+        eu_launch_contract_t3(h->grid(), h->tab, h->d_owner_hf.p, h->d_fid_of_hf.p, gravity, mg, h->d_fv.p, (long long)(h->d_fv.n/9), h->st);
     h->contracted = true;
     h->contracted_mg = mg;
     std::memcpy(h->contracted_gravity, gravity, 3*sizeof(double));
@@ -378,7 +383,7 @@ EuStepArgs step_args(eu_handle h, double dt, const double gravity[3], int n_src,
 
 bool fused_halo(eu_handle h)
 {
-    return h->cfg.world_size > 1 && h->comm_ready && h->mode == EU_MODE_FAST && h->fused_ok;
+    return h->cfg.world_size > 1 && h->comm_ready && h->mode == EU_MODE_FAST && h->fused_ok && h->tensor_fast != 2;
 }
 
 // ---- work items of the FAST kernel -----------------------------------------------------------------------
@@ -550,6 +555,10 @@ int build_items(eu_handle h, int lo, int hi)
 int launch_substep(eu_handle h, const EuStepArgs& a, bool exchange)
 {
     const EuGridDev g = h->grid();
+    if (h->mode == EU_MODE_FAST && h->tensor_fast == 2) {
+        eu_launch_fast_step_t3(g, h->tabf, h->fast(), a, h->own_lo/EU_SLICE, (h->own_hi + EU_SLICE - 1)/EU_SLICE, h->n_sms, h->st);
+        return 1;
+    }
     if (h->mode == EU_MODE_FAST) {
         const int slice_lo = h->own_lo/EU_SLICE;
         const int slice_hi = (h->own_hi + EU_SLICE - 1)/EU_SLICE;
@@ -951,9 +960,9 @@ int eu_set_fluid(eu_handle h, const eu_fluid* f)
     // there (AUTO falls back to STRICT, an explicit FAST request fails); without rock tables the tensor class is
     // isotropic (RockAnisotropicRelperm / ..._impl.hpp:86-101: the same quadratic curve in every direction) and runs
     // the scalar FAST path.
-    h->tensor_fast = false;
+    h->tensor_fast = 0;
     if (h->cfg.mode == EU_MODE_STRICT) h->mode = EU_MODE_STRICT;
-    else if (h->fast_tables_ok) { h->mode = EU_MODE_FAST; h->tensor_fast = tensor && f->n_rocks > 0; }
+    else if (h->fast_tables_ok) { h->mode = EU_MODE_FAST; h->tensor_fast = (tensor && f->n_rocks > 0) ? 1 : 0; }
     else if (h->cfg.mode == EU_MODE_FAST)
         return fail(h, EU_ERR_UNSUPPORTED, "FAST mode needs rock-table nodes at least 1/4096 apart and at most 48 curve sets");
     else h->mode = EU_MODE_STRICT;
@@ -1039,12 +1048,7 @@ int eu_grid_end(eu_handle h)
         EU_CUDA(h, cudaMemcpyAsync(&not_aligned, h->d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, h->st));
         EU_CUDA(h, cudaStreamSynchronize(h->st));
         EU_CUDA(h, cudaGetLastError());
-        if (not_aligned) {
-            if (h->cfg.mode == EU_MODE_FAST)
-                return fail(h, EU_ERR_UNSUPPORTED, "FAST mode with tensor mobility needs axis-aligned face normals");
-            h->tensor_fast = false;
-            h->mode = EU_MODE_STRICT;
-        }
+        if (not_aligned) h->tensor_fast = 2;       // oblique normals: the three-component variant (k_fast_step_t3)
     }
     EU_CUDA(h, h->d_fid_of_hf.alloc(H));
     if (h->mode == EU_MODE_STRICT) {
@@ -1093,7 +1097,11 @@ int eu_grid_end(eu_handle h)
         EU_CUDA(h, h->d_T.alloc(F));
         EU_CUDA(h, cudaMemsetAsync(h->d_qg.p, 0, F*sizeof(double2), h->st));
         EU_CUDA(h, cudaMemsetAsync(h->d_T.p, 0, F*sizeof(double), h->st));
-        if (h->tensor_fast) {
+        if (h->tensor_fast == 2) {
+            EU_CUDA(h, h->d_fv.alloc(9*F));
+            EU_CUDA(h, cudaMemsetAsync(h->d_fv.p, 0, 9*F*sizeof(double), h->st));
+        }
+        if (h->tensor_fast == 1) {
             EU_CUDA(h, h->d_axis8.alloc(F));
             EU_CUDA(h, cudaMemsetAsync(h->d_axis8.p, 0, F, h->st));
             eu_launch_face_axis(g, h->d_owner_hf.p, h->d_fid_of_hf.p, h->d_axis8.p, h->st);

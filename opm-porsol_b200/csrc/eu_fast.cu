@@ -691,6 +691,123 @@ __global__ void __launch_bounds__(kBlock, MINB) k_fast_step(EuGridDev g, EuTable
     }
 }
 
+// ---- diagonal tensor mobility on general (oblique) face normals ---------------------------------------------
+// ReservoirPropertyCapillaryAnisotropicRelperm on corner-point geometry.  With M = diag(m_x, m_y, m_z) every
+// mobility-weighted projection of the face flux (Residual_impl.hpp:205-262) is a sum over the axes,
+//   n.(M x) = sum_k n_k m_k x_k,
+// with the mobility-independent factors contracted per axis at upload (k_contract_t3: Gv, n_k^2, Tv):
+//   upstream of the non-trivial phase:  q -+ sum_k lam_t,k Gv_k          (:216-221)
+//   viscous   q sum_k n_k^2 lam_w,k / (lam_w,k + lam_o,k)                 (:241-249)
+//   gravity   sum_k Gv_k lam_w,k lam_o,k / (lam_w,k + lam_o,k)            (:252-262)
+//   capillary (pc_hi - pc_lo) sum_k Tv_k lam_w,k lam_o,k / (..) at the average saturation (:265-272)
+// The trivial phase is decided by the sign of the scalar G of the reference (:208-212), which k_contract stores.
+// One warp per slice, one face at a time from the SELL records (the structure of gather_cell_loop); the three
+// curve sets of a rock share their nodes, so one interval search serves the three axes.
+__device__ __forceinline__ void mob3(const TabLayout& L, int rock, double sat, double w[3], double o[3])
+{
+    const int s0 = 3*rock;
+    const int jrel = interval<true>(L, s0, sat) - L.offset()[s0];
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax) {
+        const double4 c = L.coef()[L.offset()[s0 + ax] + jrel];
+        w[ax] = fma(c.y, sat, c.x);
+        o[ax] = fma(c.w, sat, c.z);
+    }
+}
+
+template <bool CAP>
+__global__ void __launch_bounds__(kBlock, 2) k_fast_step_t3(EuGridDev g, EuTablesDev t, EuFastDev f, EuStepArgs a,
+                                                            int slice_lo, int slice_hi)
+{
+    TabLayout L;
+    L.nn = t.n_nodes_total; L.nb = t.n_buckets; L.shift = 0;
+    tables_to_smem(t);
+    __syncthreads();
+    {
+        const unsigned long long key = *a.fail_key;
+        if (key != ~0ULL && (unsigned)(key >> 32) < (unsigned)a.substep) return;
+    }
+    const int lane = threadIdx.x & 31;
+    const int n_warps = gridDim.x*kWarpsPerBlock;
+    for (int s = slice_lo + blockIdx.x*kWarpsPerBlock + (threadIdx.x >> 5); s < slice_hi; s += n_warps) {
+        const int c = s*EU_SLICE + lane;
+        if (c < g.own_lo || c >= g.own_hi) continue;
+        const int base = f.slice_base[s];
+        const int width = (f.slice_base[s + 1] - base) >> 5;
+        const double S0 = a.S_in[c];
+        const int rock0 = f.rock8[c];
+        const double pc0 = CAP ? a.pc_in[c] : 0.0;
+        double w0[3], o0[3];
+        mob3(L, rock0, S0, w0, o0);
+        double acc = 0.0;
+        for (int j = 0; j < width; ++j) {
+            const int2 r = f.rec[base + j*EU_SLICE + lane];
+            if (r.x == EU_REC_PAD) continue;
+            const bool interior = r.x >= 0;
+            const bool own = !interior || c < r.x;
+            const double2 qg = f.qg[r.y];
+            const double q = qg.x, G = qg.y;
+            double Gv[3], nn[3], Tv[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                Gv[k] = f.fv[(long long)k*f.fv_stride + r.y];
+                nn[k] = f.fv[(long long)(3 + k)*f.fv_stride + r.y];
+                Tv[k] = (CAP && interior) ? f.fv[(long long)(6 + k)*f.fv_stride + r.y] : 0.0;
+            }
+            const double S1 = interior ? a.S_in[r.x] : g.bnd_sat[-2 - r.x];
+            const int rock1 = interior ? f.rock8[r.x] : rock0;
+            double w1[3], o1[3];
+            mob3(L, rock1, S1, w1, o1);
+            // upstream mobilities: trivial phase by the sign of q, the other phase by the sign of q -+ sum lam_t Gv
+            const bool triv_w = G >= 0.0;
+            const bool u_self = (q >= 0.0) == own;
+            double lt[3], gsum = 0.0;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const double t0 = triv_w ? w0[k] : o0[k], t1 = triv_w ? w1[k] : o1[k];
+                lt[k] = u_self ? t0 : t1;
+                gsum = fma(lt[k], Gv[k], gsum);
+            }
+            const bool u2_self = ((triv_w ? q - gsum : q + gsum) >= 0.0) == own;
+            double visc = 0.0, grav = 0.0;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const double n0 = triv_w ? o0[k] : w0[k], n1 = triv_w ? o1[k] : w1[k];
+                const double ln = u2_self ? n0 : n1;
+                const double lw = triv_w ? lt[k] : ln;
+                const double rtot = div_pos(1.0, lt[k] + ln);
+                visc = fma(nn[k], lw*rtot, visc);
+                grav = fma(Gv[k], lt[k]*ln*rtot, grav);
+            }
+            double dS = a.method_viscous ? q*visc : 0.0;
+            if (a.method_gravity && interior) dS += grav;
+            if (CAP && interior) {
+                // mobilities at the average saturation, averaged over the two rocks (:224-239)
+                const double Sa = 0.5*(S0 + S1);
+                double wa[3], oa[3];
+                mob3(L, rock0, Sa, wa, oa);
+                if (rock1 != rock0) {
+                    double wb[3], ob[3];
+                    mob3(L, rock1, Sa, wb, ob);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) { wa[k] = 0.5*(wa[k] + wb[k]); oa[k] = 0.5*(oa[k] + ob[k]); }
+                }
+                double cap = 0.0;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) cap = fma(Tv[k], div_pos(wa[k]*oa[k], wa[k] + oa[k]), cap);
+                const double pc1 = a.pc_in[r.x];
+                dS = fma(cap, own ? (pc1 - pc0) : (pc0 - pc1), dS);
+            }
+            acc += own ? -dS : dS;
+        }
+        OwnMob<true> own0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { own0.lw[k] = w0[k]; own0.lo[k] = o0[k]; }
+        double pcn;
+        finish_cell<true, true, CAP, true>(L, t, f, a, c, S0, rock0, own0, f.inv_porevol[c], acc, pcn);
+    }
+}
+
 // capillary pressure and mobilities of a given state (start of an attempt; afterwards the substep kernel keeps
 // them current for the cells it updates, and the halo exchange for the ghosts)
 template <bool ROCKS, bool MULTIROCK>
@@ -707,7 +824,7 @@ __global__ void __launch_bounds__(kBlock) k_fast_state(EuGridDev g, EuTablesDev 
     for (int c = lo + blockIdx.x*blockDim.x + threadIdx.x; c < hi; c += gridDim.x*blockDim.x) {
         double lw, lo_, pcv;
         // (tensor mobility: table 3 r holds the pc column; the pairs are not used by that class)
-        const int table = (MULTIROCK ? f.rock8[c] : 0)*(f.axis8 ? 3 : 1);
+        const int table = (MULTIROCK ? f.rock8[c] : 0)*((f.axis8 || f.fv) ? 3 : 1);
         Mob<ROCKS, MULTIROCK>::both_and_pc(L, t, table, S[c], ROCKS ? f.pcscale[c] : 1.0, lw, lo_, pcv);
         if (pc) pc[c] = pcv;
         lam[c] = make_double2(lw, lo_);
@@ -802,6 +919,23 @@ static void launch_fast2(const EuGridDev& g, const EuTablesDev& t, const EuFastD
     else if (cap)        launch_fast<ROCKS, MULTIROCK, true, false>(g, t, f, a, halo, slice_lo, slice_hi, n_sms, smem, st);
     else if (nn)         launch_fast<ROCKS, MULTIROCK, false, true>(g, t, f, a, halo, slice_lo, slice_hi, n_sms, smem, st);
     else                 launch_fast<ROCKS, MULTIROCK, false, false>(g, t, f, a, halo, slice_lo, slice_hi, n_sms, smem, st);
+}
+
+void eu_launch_fast_step_t3(const EuGridDev& g, const EuTablesDev& t, const EuFastDev& f, const EuStepArgs& a,
+                            int slice_lo, int slice_hi, int n_sms, cudaStream_t st)
+{
+    if (slice_hi <= slice_lo) return;
+    const size_t smem = eu_fast_smem_bytes(t);
+    int blocks = n_sms*2;
+    const int need = (slice_hi - slice_lo + kWarpsPerBlock - 1)/kWarpsPerBlock;
+    if (blocks > need) blocks = need;
+    if (a.method_capillary) {
+        if (smem > 48*1024) cudaFuncSetAttribute(k_fast_step_t3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_fast_step_t3<true><<<blocks, kBlock, smem, st>>>(g, t, f, a, slice_lo, slice_hi);
+    } else {
+        if (smem > 48*1024) cudaFuncSetAttribute(k_fast_step_t3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_fast_step_t3<false><<<blocks, kBlock, smem, st>>>(g, t, f, a, slice_lo, slice_hi);
+    }
 }
 
 void eu_launch_fast_step(const EuGridDev& g, const EuTablesDev& t, const EuFastDev& f, const EuStepArgs& a,

@@ -124,6 +124,8 @@ struct EuFastDev {
     const double* pcscale;
     const unsigned char* rock8;
     const unsigned char* axis8;  // per unique face: axis of its (axis-aligned) normal -- FAST tensor mobility only, else NULL
+    const double* fv;            // FAST tensor mobility on oblique normals: fv[k*fv_stride + face], k = 0..2 Gv, 3..5 n_k^2,
+    long long fv_stride;         // 6..8 Tv (k_contract_t3); else NULL
     long long F;
     int prefetch;             // marches request the next cell's lines into L2 one step ahead
 };
@@ -185,6 +187,8 @@ void eu_launch_contract(const EuGridDev& g, const EuTablesDev& t, const int* own
                         const double gravity[3], int method_gravity, double* G, double* T, double* nn,
                         double* nn_maxdev, cudaStream_t st);
 // tensor mobility in FAST mode: are all face normals axis-aligned (flag[0] |= 1 if not)?  axis per unique face
+void eu_launch_contract_t3(const EuGridDev& g, const EuTablesDev& t, const int* owner_hf, const int* fid_of_hf,
+                           const double gravity[3], int method_gravity, double* fv, long long stride, cudaStream_t st);
 void eu_launch_axis_check(const EuGridDev& g, int* flag, cudaStream_t st);
 void eu_launch_face_axis(const EuGridDev& g, const int* owner_hf, const int* fid_of_hf, unsigned char* axis8, cudaStream_t st);
 void eu_launch_pcscale(const EuGridDev& g, const EuTablesDev& t, double* pcscale, unsigned char* rock8, double* inv_porevol, cudaStream_t st);
@@ -215,6 +219,8 @@ void eu_launch_fast_state(const EuGridDev& g, const EuTablesDev& t, const EuFast
                           double2* lam, int lo, int hi, cudaStream_t st);
 void eu_launch_fast_step(const EuGridDev& g, const EuTablesDev& t, const EuFastDev& f, const EuStepArgs& a,
                          const EuHaloDev& halo, int slice_lo, int slice_hi, int n_sms, cudaStream_t st);
+void eu_launch_fast_step_t3(const EuGridDev& g, const EuTablesDev& t, const EuFastDev& f, const EuStepArgs& a,
+                            int slice_lo, int slice_hi, int n_sms, cudaStream_t st);
 void eu_launch_ghost_adjacent(const EuGridDev& g, int* out4, cudaStream_t st);
 size_t eu_fast_smem_bytes(const EuTablesDev& t);
 

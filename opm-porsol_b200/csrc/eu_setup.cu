@@ -367,6 +367,53 @@ __global__ void k_face_axis(EuGridDev g, const int* __restrict__ owner_hf, const
     axis8[fid_of_hf[h]] = (unsigned char)normal_axis(g.hf_normal + 3*h, &aligned);
 }
 
+// Static per-face vectors of the FAST path for diagonal tensor mobility on general (oblique) normals: with
+// M = diag(m_x, m_y, m_z) the terms of the face flux (Residual_impl.hpp:205-262) are sums over the axes,
+//   n.(M x) = sum_k n_k m_k x_k,
+// so the mobility-independent factors are kept per axis: Gv_k = area n_k ((K g) drho)_k, nn_k = n_k^2,
+// Tv_k = area n_k (K dhat)_k / (d0 + d1).  Layout: fv[k*stride + face], k = 0..2 Gv, 3..5 nn, 6..8 Tv.
+__global__ void k_contract_t3(EuGridDev g, EuTablesDev t, const int* __restrict__ owner_hf, const int* __restrict__ fid_of_hf,
+                              double gx, double gy, double gz, int method_gravity, double* __restrict__ fv, long long stride)
+{
+    int c = blockIdx.x*blockDim.x + threadIdx.x;
+    if (c >= g.n_local) return;
+    const int b = g.hf_offset[c], e = g.hf_offset[c + 1];
+    const double gravity[3] = { gx, gy, gz };
+    for (int h = b; h < e; ++h) {
+        if (owner_hf[h] != h) continue;
+        const int fid = fid_of_hf[h];
+        const int n = g.hf_nbr[h];
+        int c1 = c, nbhf = h;
+        bool interior_like = true;
+        if (n >= 0) {
+            c1 = n;
+        } else {
+            const int bi = -2 - n;
+            if (g.bnd_kind[bi] == EU_HF_PERIODIC) { c1 = g.bnd_partner_cell[bi]; nbhf = g.bnd_partner_hf[bi]; }
+            else interior_like = false;
+        }
+        double aver[9];
+        sm_aver9(g.perm + 9LL*c, g.perm + 9LL*c1, aver);
+        double gi[3];
+        sm_prod3(aver, gravity, gi);
+        for (int i = 0; i < 3; ++i) gi[i] *= t.delta_rho;
+        const double area = g.hf_area[h];
+        const double nrm[3] = { g.hf_normal[3LL*h], g.hf_normal[3LL*h + 1], g.hf_normal[3LL*h + 2] };
+        double ci[3] = { 0.0, 0.0, 0.0 }, d0d1 = 1.0;
+        if (interior_like) {
+            double dirhat[3];
+            sm_cap_direction(g.cell_centroid + 3LL*c, g.cell_centroid + 3LL*c1, g.hf_centroid + 3LL*h,
+                             g.hf_centroid + 3LL*nbhf, dirhat, &d0d1);
+            sm_prod3(aver, dirhat, ci);
+        }
+        for (int k = 0; k < 3; ++k) {
+            fv[(long long)k*stride + fid] = method_gravity ? area*(nrm[k]*gi[k]) : 0.0;
+            fv[(long long)(3 + k)*stride + fid] = nrm[k]*nrm[k];
+            fv[(long long)(6 + k)*stride + fid] = interior_like ? area*(nrm[k]*ci[k])/d0d1 : 0.0;
+        }
+    }
+}
+
 __global__ void k_pcscale(EuGridDev g, EuTablesDev t, double* __restrict__ pcscale, unsigned char* __restrict__ rock8,
                           double* __restrict__ inv_porevol)
 {
@@ -791,6 +838,12 @@ void eu_launch_contract(const EuGridDev& g, const EuTablesDev& t, const int* own
     cudaMemsetAsync(nn_maxdev, 0, sizeof(double), st);
     k_contract<<<div_up(g.n_local, kThreads), kThreads, 0, st>>>(g, t, owner_hf, fid_of_hf, gravity[0], gravity[1], gravity[2],
                                                                  method_gravity, G, T, nn, (unsigned long long*)nn_maxdev);
+}
+void eu_launch_contract_t3(const EuGridDev& g, const EuTablesDev& t, const int* owner_hf, const int* fid_of_hf,
+                           const double gravity[3], int method_gravity, double* fv, long long stride, cudaStream_t st)
+{
+    k_contract_t3<<<div_up(g.n_local, kThreads), kThreads, 0, st>>>(g, t, owner_hf, fid_of_hf, gravity[0], gravity[1], gravity[2],
+                                                                    method_gravity, fv, stride);
 }
 void eu_launch_axis_check(const EuGridDev& g, int* flag, cudaStream_t st)
 {

@@ -101,54 +101,39 @@ def test_tensor_mobility_strict(name, case):
 
 
 @pytest.mark.parametrize("mode", ["fast", "auto"])
-@pytest.mark.parametrize("name,case", tensor_aligned_cases(), ids=[n for n, _ in tensor_aligned_cases()])
+@pytest.mark.parametrize("name,case", TENSOR_ALL, ids=[n for n, _ in TENSOR_ALL])
 def test_tensor_mobility_fast(name, case, mode):
-    """FAST mode for the diagonal tensor mobility on axis-aligned grids: per-substep and per-transportSolve gates,
-    bit-exact CFL times and identical step counts, like the scalar class."""
+    """FAST mode for the diagonal tensor mobility, on axis-aligned grids (scalar formula with the face axis' mobility
+    component) and on oblique normals (three-component kernel): per-substep and per-transportSolve gates, bit-exact
+    CFL times and identical step counts, like the scalar class."""
+    import copy
+    case = copy.copy(case)
+    # The capillary CFL factor of the reference's tensor class is not a usable number (~1e-89 s steps, see
+    # tests/golden/make_golden.py): fixed 50 s substeps, 18 of them per transportSolve, exercise the update instead.
+    case.min_steps = case.max_steps = 18
     dev, port = _solvers(case, mode)
     assert dev.resolved_mode() == "fast"
     dev.upload_state(case.sat0, case.hf_flux)
-    cfl_cpu = port.cfl_times()
-    assert np.array_equal(dev.cfl_times(case.gravity), cfl_cpu)
+    assert np.array_equal(dev.cfl_times(case.gravity), port.cfl_times())
     inj = (case.src_cell, case.src_rate)
-    total = active_cfl_dt(case, cfl_cpu)
     s_cpu = case.sat0.copy()
+    moved = 0.0
     for q in range(3):
-        a = port.small_step(s_cpu, 0.5*total)
-        b = dev.small_step(0.5*total, case.gravity, inj)
+        a = port.small_step(s_cpu, 50.0)
+        b = dev.small_step(50.0, case.gravity, inj)
+        moved = max(moved, float(np.abs(a["sat"] - s_cpu).max()))
         s_cpu = a["sat"]
         assert a["status"] == 0 and b["status"] == 0
         assert np.abs(dev.download_saturation() - s_cpu).max() <= TOL_SUBSTEP
         assert np.abs(b["residual"] - a["residual"]).max() <= 1e-12*(np.abs(a["residual"]).max() + 1e-300)
         dev.upload_saturation(s_cpu)
-    time = 17.3*total
-    a = port.transport_solve(case.sat0, time=time)
+    assert moved > 1e-6, "the substeps are meant to change the saturation"
+    a = port.transport_solve(case.sat0, time=900.0)
     sat = case.sat0.copy()
-    rep = dev.transportSolve(sat, time, case.gravity, case.hf_flux, inj)
-    assert a["status"] == 0 and rep.status == 0 and rep.nsteps == a["nsteps"] == 18 and rep.attempts == a["attempts"]
-    assert np.abs(sat - a["sat"]).max() <= TOL_SOLVE
-    dev.close()
-
-
-def test_tensor_fast_refuses_oblique_normals():
-    """Explicit FAST with tensor rock tables on a grid with oblique normals is refused; AUTO falls back to STRICT."""
-    from opm_porsol_b200 import EulerB200Error, EulerUpstream
-    from opm_porsol_b200.binding import params_from_case
-    from oracle.ref import RefSolver, ref_available
-    if not ref_available():
-        pytest.skip("tensor-mobility CFL factors come from the compiled reference")
-    name, case = tensor_cases()[0]
-    fac = RefSolver(case).cfl_factors()
-    dev = EulerUpstream(device=0, mode="fast")
-    dev.init(params_from_case(case))
-    with pytest.raises(EulerB200Error) as ei:
-        dev.initObj(case, cfl_factors=fac)
-    assert ei.value.code == 5
-    dev.close()
-    dev = EulerUpstream(device=0, mode="auto")
-    dev.init(params_from_case(case))
-    dev.initObj(case, cfl_factors=fac)
-    assert dev.resolved_mode() == "strict"
+    rep = dev.transportSolve(sat, 900.0, case.gravity, case.hf_flux, inj, raise_on_error=False)
+    assert (rep.status != 0) == (a["status"] != 0) and rep.nsteps == a["nsteps"] == 18 and rep.attempts == a["attempts"]
+    if a["status"] == 0:
+        assert np.abs(sat - a["sat"]).max() <= TOL_SOLVE
     dev.close()
 
 

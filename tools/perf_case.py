@@ -4,6 +4,7 @@
     python tools/perf_case.py c2 --n 160          # n^3 Cartesian, rotated anisotropic K, rock table, V+G+C
     python tools/perf_case.py c2b --n 160         # the same with diagonal tensor mobility (aniso_simulator_test's class)
     python tools/perf_case.py c3 --dims 256 256 128   # faulted corner-point, lognormal K, 3 rocks, V+G+C
+    python tools/perf_case.py t3 --n 100          # tensor mobility on randomised oblique normals (three-component kernel)
 
 Prints cell-substeps/s of the resident transportSolve with a fixed number of substeps, the algorithmic-byte
 roofline fraction (a*N + 8*N_hf + b*N_f) and FAST-vs-STRICT agreement after the run."""
@@ -21,7 +22,7 @@ import numpy as np  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("case", choices=["c2", "c2b", "c3"])
+    ap.add_argument("case", choices=["c2", "c2b", "c3", "t3"])
     ap.add_argument("--n", type=int, default=160)
     ap.add_argument("--dims", type=int, nargs=3, default=[256, 256, 128])
     ap.add_argument("--substeps", type=int, default=50)
@@ -33,7 +34,13 @@ def main():
     from opm_porsol_b200 import synth
     from opm_porsol_b200.binding import make_fluid, params_from_case
     t0 = time.time()
-    if a.case == "c2b":
+    if a.case == "t3":
+        # tensor mobility on oblique normals (three-component FAST kernel): randomised geometry, 2 rocks
+        twin = synth.config_c2(8)
+        fluid, _ = make_fluid(twin)
+        fac = np.array(fluid.cfl_factor[:])
+        case = synth.random_geometry_case(a.n, a.n, a.n, seed=5, n_rocks=2, mobility_kind=1, sources=False)
+    elif a.case == "c2b":
         # tensor mobility: the CFL factors of the scalar twin stand in for the reference's (the step count is fixed here)
         twin = synth.config_c2(8)
         fluid, _ = make_fluid(twin)
