@@ -109,7 +109,8 @@ struct eu_solver {
     long long F = 0;
     int n_slices = 0;
     bool use_nn = false;
-    int prefetch = 1;                  // EU_PREFETCH=0 turns the L2 prefetch of the marches off (tuning knob)
+    int prefetch = 1;                  // EU_PREFETCH=<march steps ahead>, 0 turns the L2 prefetch of the marches off (tuning knob)
+    int l2_hint = 1;                   // EU_L2_HINT=0 turns the evict-first L2 policy of the streaming arrays off (tuning knob)
     bool contracted = false;
     double contracted_gravity[3] = { 0, 0, 0 };
     int contracted_mg = -1;
@@ -184,6 +185,7 @@ struct eu_solver {
         f.fv = tensor_fast == 2 ? d_fv.p : nullptr;
         f.fv_stride = (long long)(d_fv.n/9);
         f.prefetch = prefetch;
+        f.l2_hint = l2_hint;
         return f;
     }
     int global_to_local(int gcell) const
@@ -723,7 +725,8 @@ int eu_create(const eu_config* cfg, eu_handle* out)
     eu_default_params(&h->par);
     h->mode = EU_MODE_STRICT;
     h->n_sms = prop.multiProcessorCount;
-    { const char* e = getenv("EU_PREFETCH"); if (e) h->prefetch = atoi(e) != 0; }
+    { const char* e = getenv("EU_PREFETCH"); if (e) h->prefetch = std::min(std::max(atoi(e), 0), 8); }
+    { const char* e = getenv("EU_L2_HINT"); if (e) h->l2_hint = atoi(e) != 0; }
     { const char* e = getenv("EU_PIN_CACHE"); if (e) h->pin_cache = atoi(e) != 0; }
     std::memset(&h->fluid, 0, sizeof(h->fluid));
     std::memset(&h->tab, 0, sizeof(h->tab));
@@ -1109,7 +1112,7 @@ int eu_grid_end(eu_handle h)
         EU_CUDA(h, h->d_pcscale.alloc(n));
         EU_CUDA(h, h->d_rock8.alloc(n));
         EU_CUDA(h, h->d_inv_porevol.alloc(n));
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < 2 && eu_fast_uses_stored_lam(); ++k) {
             EU_CUDA(h, h->d_lam[k].alloc(n));
             EU_CUDA(h, cudaMemsetAsync(h->d_lam[k].p, 0, n*sizeof(double2), h->st));
         }

@@ -19,6 +19,16 @@
 
 namespace {
 
+// Neighbour mobilities in the marches: recomputed from the neighbours' saturations (five rock-curve lookups per cell,
+// the default), or loaded as {lambda_w, lambda_o} pairs the previous substep stored (one lookup per cell, but 32 more
+// bytes of HBM traffic per cell and substep: -DEU_STORED_LAM).  Build-time choice, measured both ways on B200
+// (DESIGN.md section 5): recomputing is 10 % faster on the V+G bench grid and 1-5 % with the capillary term.
+#ifdef EU_STORED_LAM
+constexpr bool kStoredLam = true;
+#else
+constexpr bool kStoredLam = false;
+#endif
+
 constexpr int kWarpsPerBlock = 8;
 constexpr int kBlock = kWarpsPerBlock*32;
 
@@ -388,6 +398,13 @@ __device__ __forceinline__ double finish_cell(const TabLayout& L, const EuTables
         }
         return sat;
     }
+    if (!kStoredLam) {           // no pair arrays: only the capillary pressure of the new state
+        if (CAP) {
+            pcn = Mob<ROCKS, MULTIROCK>::pc(L, rock0, sat, ROCKS ? f.pcscale[c] : 1.0);
+            a.pc_out[c] = pcn;
+        }
+        return sat;
+    }
     if (CAP) {
         Mob<ROCKS, MULTIROCK>::both_and_pc(L, t, rock0, sat, ROCKS ? f.pcscale[c] : 1.0, lwn, lon, pcn);
         a.pc_out[c] = pcn;
@@ -422,6 +439,27 @@ __device__ __forceinline__ void prefetch_l2(const void* p)
 {
     asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
 }
+// L2 eviction policy for the arrays a substep streams through exactly once ({q, G} pairs, 1/porevol, T): evict-first,
+// so that they do not displace the neighbours' mobility pairs other warps are about to read.
+__device__ __forceinline__ unsigned long long stream_policy(bool evict_first)
+{
+    unsigned long long p;
+    if (evict_first) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    else             asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ double2 ldg_pair_stream(const double2* p, unsigned long long pol)
+{
+    double2 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ double ldg_f64_stream(const double* p, unsigned long long pol)
+{
+    double v;
+    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    return v;
+}
 
 // state carried along a march
 struct MarchCarry {
@@ -450,12 +488,20 @@ __device__ __forceinline__ void march_head(const TabLayout& L, const EuTablesDev
 {
     const int nb = c + cl->nb_off[4];
     const int fid = c*cl->fid_mul[4] + cl->fid_off[4];
-    const double2 lam0 = ldg_pair(a.lam_in + c), lam1 = ldg_pair(a.lam_in + nb), qg = ldg_pair(f.qg + fid);
+    double2 lam0, lam1;
+    const double2 qg = ldg_pair(f.qg + fid);
     m.S0 = ldg_f64(a.S_in + c);
-    const double S1 = CAP ? __ldg(a.S_in + nb) : 0.0;
+    const double S1 = (CAP || !kStoredLam) ? __ldg(a.S_in + nb) : 0.0;
     const double nn = NN ? __ldg(f.nn + fid) : 1.0;
     m.rock0 = MULTIROCK ? __ldg(f.rock8 + c) : 0;
-    const int rk1 = (MULTIROCK && CAP) ? __ldg(f.rock8 + nb) : 0;
+    const int rk1 = (MULTIROCK && (CAP || !kStoredLam)) ? __ldg(f.rock8 + nb) : 0;
+    if (kStoredLam) {
+        lam0 = ldg_pair(a.lam_in + c);
+        lam1 = ldg_pair(a.lam_in + nb);
+    } else {
+        Mob<ROCKS, MULTIROCK>::both(L, t, m.rock0, m.S0, lam0.x, lam0.y);
+        Mob<ROCKS, MULTIROCK>::both(L, t, rk1, S1, lam1.x, lam1.y);
+    }
     m.pc0 = CAP ? __ldg(a.pc_in + c) : 0.0;
     const double T = CAP ? __ldg(f.T + fid) : 0.0, pc1 = CAP ? __ldg(a.pc_in + nb) : 0.0;
     m.lw0 = lam0.x; m.lo0 = lam0.y;
@@ -465,9 +511,10 @@ __device__ __forceinline__ void march_head(const TabLayout& L, const EuTablesDev
 // one cell of a march; advances the carry to the cell across slot 5
 template <bool ROCKS, bool MULTIROCK, bool CAP, bool NN, bool RECORDS>
 __device__ __forceinline__ void march_step(const TabLayout& L, const EuGridDev& g, const EuTablesDev& t, const EuFastDev& f,
-                                           const EuStepArgs& a, const EuSliceClass* __restrict__ cl, int c, int lane, bool more,
+                                           const EuStepArgs& a, const EuSliceClass* __restrict__ cl, int c, int lane, int ahead,
                                            MarchCarry& m)
 {
+    const unsigned long long pol = stream_policy(f.l2_hint != 0);     // (live only while the loads are issued)
     constexpr int kOrder[5] = { 5, 3, 2, 1, 0 };       // far neighbours first: their lines take longest to arrive
     int nb[6], fid[6];
     double2 lam[6], qg[6];
@@ -476,19 +523,24 @@ __device__ __forceinline__ void march_step(const TabLayout& L, const EuGridDev& 
         const int j = kOrder[k];
         nb[j] = c + cl->nb_off[j];
         fid[j] = c*cl->fid_mul[j] + cl->fid_off[j];
-        lam[j] = ldg_pair(a.lam_in + nb[j]);
-        qg[j] = ldg_pair(f.qg + fid[j]);
+        if (kStoredLam) lam[j] = ldg_pair(a.lam_in + nb[j]);
+        qg[j] = ldg_pair_stream(f.qg + fid[j], pol);
     }
     const double S5 = ldg_f64(a.S_in + nb[5]);
-    const double inv_pv = ldg_f64(f.inv_porevol + c);
-    if (f.prefetch && more) {
+    const double inv_pv = ldg_f64_stream(f.inv_porevol + c, pol);
+    if (ahead > 0) {
         // the lines the next cell of the march (c + D) will load, requested into L2 now: its z+ and y neighbours'
         // mobility pairs (the x neighbours share the lines of lam[c + D], loaded above as slot 5), the {q, G} pairs of
         // its faces, its z+ neighbour's saturation and its 1/porevol.  No registers are tied up by these requests.
-        const int D = cl->D;
-        prefetch_l2(a.lam_in + nb[5] + D);
-        prefetch_l2(a.lam_in + nb[3] + D);
-        prefetch_l2(a.lam_in + nb[2] + D);
+        const int D = cl->D*ahead;
+        if (kStoredLam) {
+            prefetch_l2(a.lam_in + nb[5] + D);
+            prefetch_l2(a.lam_in + nb[3] + D);
+            prefetch_l2(a.lam_in + nb[2] + D);
+        } else {
+            prefetch_l2(a.S_in + nb[3] + D);
+            prefetch_l2(a.S_in + nb[2] + D);
+        }
         prefetch_l2(f.qg + fid[5] + D*cl->fid_mul[5]);
         prefetch_l2(f.qg + fid[3] + D*cl->fid_mul[3]);
         prefetch_l2(f.qg + fid[2] + D*cl->fid_mul[2]);
@@ -508,11 +560,18 @@ __device__ __forceinline__ void march_step(const TabLayout& L, const EuGridDev& 
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
         const int j = kOrder[k];
-        S1[j] = (CAP && j != 5) ? __ldg(a.S_in + nb[j]) : S5;
-        rk[j] = (MULTIROCK && (CAP || j == 5)) ? __ldg(f.rock8 + nb[j]) : 0;
+        S1[j] = ((CAP || !kStoredLam) && j != 5) ? __ldg(a.S_in + nb[j]) : S5;
+        rk[j] = (MULTIROCK && (CAP || !kStoredLam || j == 5)) ? __ldg(f.rock8 + nb[j]) : 0;
         nn[j] = NN ? __ldg(f.nn + fid[j]) : 1.0;
         T[j] = CAP ? __ldg(f.T + fid[j]) : 0.0;
         pc1[j] = CAP ? __ldg(a.pc_in + nb[j]) : 0.0;
+    }
+    if (!kStoredLam) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const int j = kOrder[k];
+            Mob<ROCKS, MULTIROCK>::both(L, t, rk[j], S1[j], lam[j].x, lam[j].y);
+        }
     }
     double acc = m.dS4;                 // self is the hi cell of the slot-4 face: +dS
 #ifdef EU_EXP_NOARITH               // timing experiment: the memory access pattern without the face arithmetic
@@ -555,7 +614,9 @@ __device__ __forceinline__ void march_item_impl(const TabLayout& L, const EuGrid
     MarchCarry m;
     march_head<ROCKS, MULTIROCK, CAP, NN>(L, t, f, a, cl, c, m);
     for (int i = 0; i < len; ++i) {
-        march_step<ROCKS, MULTIROCK, CAP, NN, RECORDS>(L, g, t, f, a, cl, c, lane, i + 1 < len, m);
+        // prefetch distance in march steps (0 = off); never past the last cell of the item
+        const int ahead = (i + f.prefetch < len) ? f.prefetch : 0;
+        march_step<ROCKS, MULTIROCK, CAP, NN, RECORDS>(L, g, t, f, a, cl, c, lane, ahead, m);
         c += D;
     }
 }
@@ -827,11 +888,13 @@ __global__ void __launch_bounds__(kBlock) k_fast_state(EuGridDev g, EuTablesDev 
         const int table = (MULTIROCK ? f.rock8[c] : 0)*((f.axis8 || f.fv) ? 3 : 1);
         Mob<ROCKS, MULTIROCK>::both_and_pc(L, t, table, S[c], ROCKS ? f.pcscale[c] : 1.0, lw, lo_, pcv);
         if (pc) pc[c] = pcv;
-        lam[c] = make_double2(lw, lo_);
+        if (lam) lam[c] = make_double2(lw, lo_);
     }
 }
 
 } // namespace
+
+bool eu_fast_uses_stored_lam() { return kStoredLam; }
 
 size_t eu_fast_smem_bytes(const EuTablesDev& t)
 {
@@ -843,7 +906,7 @@ size_t eu_fast_smem_bytes(const EuTablesDev& t)
 void eu_launch_fast_state(const EuGridDev& g, const EuTablesDev& t, const EuFastDev& f, const double* S, double* pc,
                           double2* lam, int lo, int hi, cudaStream_t st)
 {
-    if (hi <= lo) return;
+    if (hi <= lo || (!pc && !lam)) return;
     const size_t smem = eu_fast_smem_bytes(t);
     int blocks = (hi - lo + kBlock - 1)/kBlock;
     if (blocks > 148*8) blocks = 148*8;

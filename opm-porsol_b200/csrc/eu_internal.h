@@ -127,7 +127,8 @@ struct EuFastDev {
     const double* fv;            // FAST tensor mobility on oblique normals: fv[k*fv_stride + face], k = 0..2 Gv, 3..5 n_k^2,
     long long fv_stride;         // 6..8 Tv (k_contract_t3); else NULL
     long long F;
-    int prefetch;             // marches request the next cell's lines into L2 one step ahead
+    int prefetch;             // marches request a later cell's lines into L2: distance in march steps, 0 = off
+    int l2_hint;              // streaming arrays are loaded with an evict-first L2 policy
 };
 
 struct EuStepArgs {
@@ -142,7 +143,7 @@ struct EuStepArgs {
     double* S_out;
     const double* pc_in;      // FAST: pc(S_in) for all local cells; STRICT: scratch filled by k_strict_pc
     double* pc_out;
-    const double2* lam_in;    // FAST: {lambda_w, lambda_o}(S_in) of the own cells (the marches read their neighbours' pairs)
+    const double2* lam_in;    // FAST built with -DEU_STORED_LAM: {lambda_w, lambda_o}(S_in) of the own cells; else NULL
     double2* lam_out;
     double* residual_out;     // optional
     unsigned long long* fail_key;   // min over failing (substep<<32 | local cell)
@@ -223,5 +224,6 @@ void eu_launch_fast_step_t3(const EuGridDev& g, const EuTablesDev& t, const EuFa
                             int slice_lo, int slice_hi, int n_sms, cudaStream_t st);
 void eu_launch_ghost_adjacent(const EuGridDev& g, int* out4, cudaStream_t st);
 size_t eu_fast_smem_bytes(const EuTablesDev& t);
+bool eu_fast_uses_stored_lam();      // build-time choice of eu_fast.cu: per-cell mobility pairs kept in HBM
 
 #endif

@@ -40,6 +40,7 @@ def main():
         fluid, _ = make_fluid(twin)
         fac = np.array(fluid.cfl_factor[:])
         case = synth.random_geometry_case(a.n, a.n, a.n, seed=5, n_rocks=2, mobility_kind=1, sources=False)
+        case.clamp_sat = True          # randomised (unphysical) geometry: keep the run going, this case only times the kernel
     elif a.case == "c2b":
         # tensor mobility: the CFL factors of the scalar twin stand in for the reference's (the step count is fixed here)
         twin = synth.config_c2(8)
