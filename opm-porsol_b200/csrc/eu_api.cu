@@ -482,13 +482,52 @@ int build_items(eu_handle h, int lo, int hi)
         }
         cls[size_t(s - lo)] = (unsigned short)id;
     }
-    // chains along the march direction
+    // Chains along the march direction, cut into work items.  The persistent grid hands item v to warp v mod #warps, so
+    // the kernel ends when the warp with the most march steps ends: the piece length L is chosen to minimise
+    //     ceil(#items / #warps) * (mean piece length + head)
+    // (head = the extra face and loads of the first cell of a march, about a third of a step) over L = 4..64, and every
+    // chain is cut into ceil(n/L) pieces of nearly equal length.  A fixed L = 32 left 8 % of the warps' time idle on a
+    // 128-plane slab (9.2 items per warp -> 10).  EU_MARCH_LEN overrides L.
     const int n_warps = h->n_sms*32;
+    auto chain_length = [&](int s, int id, const std::vector<char>& taken) {
+        int n = 1;
+        const int step = classes[size_t(id)].D/EU_SLICE;
+        if (step <= 0) return 1;
+        for (int nxt = s + step; n < 65535 && nxt < hi && !taken[size_t(nxt - lo)] && cls[size_t(nxt - lo)] == id; nxt += step) ++n;
+        return n;
+    };
     int lmax = 32;
     {
         const char* e = getenv("EU_MARCH_LEN");
-        if (e && atoi(e) > 0) lmax = std::min(atoi(e), 4096);
-        else while (lmax > 2 && (hi - lo)/lmax < 6*n_warps) lmax /= 2;
+        if (e && atoi(e) > 0) {
+            lmax = std::min(atoi(e), 4096);
+        } else {
+            // chain lengths (a dry run of the scan below with unlimited pieces)
+            std::vector<int> chain_n;
+            long long n_generic = 0;
+            {
+                std::vector<char> seen(cls.size(), 0);
+                for (int s = lo; s < hi; ++s) {
+                    if (seen[size_t(s - lo)]) continue;
+                    const int id = cls[size_t(s - lo)];
+                    if (id == EU_ITEM_GENERIC) { ++n_generic; continue; }
+                    const int n = chain_length(s, id, seen);
+                    const int step = std::max(classes[size_t(id)].D/EU_SLICE, 1);
+                    for (int k = 0; k < n; ++k) seen[size_t(s + k*step - lo)] = 1;
+                    chain_n.push_back(n);
+                }
+            }
+            double best = 1e300;
+            for (int L = 4; L <= 64; ++L) {
+                long long pieces = 0, steps = 0;
+                for (int n : chain_n) { pieces += (n + L - 1)/L; steps += n; }
+                if (pieces == 0) break;
+                const long long items_total = pieces + n_generic;
+                const double per_warp = double((items_total + n_warps - 1)/n_warps);
+                const double cost = per_warp*(double(steps)/double(pieces) + 0.35);
+                if (cost <= best) { best = cost; lmax = L; }
+            }
+        }
     }
     std::vector<int2> items;
     std::vector<char> taken(cls.size(), 0);
@@ -500,12 +539,11 @@ int build_items(eu_handle h, int lo, int hi)
         if (id != EU_ITEM_GENERIC) {
             const int step = classes[size_t(id)].D/EU_SLICE;
             if (step > 0) {
-                int nxt = s + step;
-                while (len < lmax && nxt < hi && !taken[size_t(nxt - lo)] && cls[size_t(nxt - lo)] == id) {
-                    taken[size_t(nxt - lo)] = 1;
-                    ++len;
-                    nxt += step;
-                }
+                // this piece: an equal share of what is left of the chain
+                const int left = chain_length(s, id, taken);
+                const int pieces = (left + lmax - 1)/lmax;
+                len = (left + pieces - 1)/pieces;
+                for (int k = 1; k < len; ++k) taken[size_t(s + k*step - lo)] = 1;
             }
             n_class_slices += len;
         }
