@@ -487,7 +487,10 @@ int build_items(eu_handle h, int lo, int hi)
     //     ceil(#items / #warps) * (mean piece length + head)
     // (head = the extra face and loads of the first cell of a march, about a third of a step) over L = 4..64, and every
     // chain is cut into ceil(n/L) pieces of nearly equal length.  A fixed L = 32 left 8 % of the warps' time idle on a
-    // 128-plane slab (9.2 items per warp -> 10).  EU_MARCH_LEN overrides L.
+    // 128-plane slab (9.2 items per warp -> 10).  EU_MARCH_LEN overrides L.  Measured (profiles/README.md): +5-7 % on
+    // single-rank grids of 32-128 planes, neutral at 256; on a 2-rank run the long pieces this rule picks there (63
+    // steps) were 10 % slower than L = 32, so decomposed runs keep the fixed rule (L = 32, halved while a warp would
+    // get fewer than 6 items) until that is understood.
     const int n_warps = h->n_sms*32;
     auto chain_length = [&](int s, int id, const std::vector<char>& taken) {
         int n = 1;
@@ -501,6 +504,8 @@ int build_items(eu_handle h, int lo, int hi)
         const char* e = getenv("EU_MARCH_LEN");
         if (e && atoi(e) > 0) {
             lmax = std::min(atoi(e), 4096);
+        } else if (h->cfg.world_size > 1) {
+            while (lmax > 2 && (hi - lo)/lmax < 6*n_warps) lmax /= 2;
         } else {
             // chain lengths (a dry run of the scan below with unlimited pieces)
             std::vector<int> chain_n;
