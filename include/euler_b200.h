@@ -274,6 +274,16 @@ int eu_comm_plan_sends(int own_begin, int own_end, int n_ghost, const int* ghost
 int eu_compute_cfl_factors(const eu_fluid* fluid, int n_cells, const double* porosity,
                            const double* permeability, const int* rock_id, double out[3]);
 
+/* ---- host-side helper, no device needed: periodic partner matching of boundary faces, findPeriodicPartners
+ *      (BoundaryPeriodicity.hpp:86-177) with match() (BoundaryPeriodicity.cpp:25-49) -- the step that produces the
+ *      partner table behind eu_grid_chunk::bnd_partner_*.  Faces in the order the grid walk meets them.
+ * in:  centroid[3n], area[n], is_periodic[6] (xmin, xmax, ymin, ...), spatial_tolerance (1e-6 in the reference)
+ * out: canon_pos[n] (0 xmin, 1 xmax, 2 ymin, ...), partner[n] (index of the partner face, -1 if none), side_areas[6]
+ * Returns EU_ERR_ARG when a centroid is not on the bounding box of all centroids (the reference throws).
+ * O(n log n); identical to the reference wherever exactly one face qualifies as partner. */
+int eu_match_periodic_faces(int n, const double* centroid, const double* area, const int is_periodic[6],
+                            double spatial_tolerance, int* canon_pos, int* partner, double side_areas[6]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -113,3 +113,68 @@ extern "C" int eu_compute_cfl_factors(const eu_fluid* fluid, int n_cells, const 
     }
     return EU_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Periodic partner matching of boundary faces: findPeriodicPartners (common/BoundaryPeriodicity.hpp:86-177) with
+// match() (common/BoundaryPeriodicity.cpp:25-49), the host-side step that produces the partner table the transport
+// path consumes (eu_grid_chunk::bnd_partner_*).  Same definitions as the reference: bounding box of the face
+// centroids; canonical side = the first coordinate direction whose low (then high) bound the centroid touches within
+// the spatial tolerance; partners sit on opposite sides, have areas within 1e-6 and centroids -- with the normal
+// coordinate zeroed -- within 1e-6 of each other.  The reference sorts the faces by a scalar key
+// (c_a + pi c_b of the two transverse coordinates), looks 10 places either way and falls back to a scan over all
+// faces, O(n^2) when many faces have no partner; here every candidate within the tolerance is found in the sorted key
+// band [key - (1 + pi) tol, key + (1 + pi) tol], O(n log n) on the 1 M boundary faces of the 67 M-cell grid.
+// Where exactly one face qualifies -- every well-posed periodic grid -- the result is the reference's.
+extern "C" int eu_match_periodic_faces(int n, const double* centroid, const double* area, const int is_periodic[6],
+                                       double spatial_tolerance, int* canon_pos, int* partner, double side_areas[6])
+{
+    if (n < 0 || (n > 0 && (!centroid || !area)) || !is_periodic || !canon_pos || !partner || !side_areas) return EU_ERR_ARG;
+    const double pi = 3.14159265358979323846264338327950288;
+    const double area_tol = 1e-6, centroid_tol = 1e-6;
+    double low[3] = { 1e100, 1e100, 1e100 }, hi[3] = { -1e100, -1e100, -1e100 };
+    for (int i = 0; i < n; ++i) {
+        for (int d = 0; d < 3; ++d) {
+            low[d] = std::min(low[d], centroid[3*size_t(i) + d]);
+            hi[d] = std::max(hi[d], centroid[3*size_t(i) + d]);
+        }
+    }
+    for (int k = 0; k < 6; ++k) side_areas[k] = 0.0;
+    const size_t nn = size_t(n);
+    std::vector<double> cent(3*nn), key(nn);
+    for (int i = 0; i < n; ++i) {
+        int cp = -1;
+        for (int d = 0; d < 3; ++d) {
+            const double coord = centroid[3*size_t(i) + d];
+            if (std::fabs(coord - low[d]) <= spatial_tolerance) { cp = 2*d; break; }
+            if (std::fabs(coord - hi[d]) <= spatial_tolerance) { cp = 2*d + 1; break; }
+        }
+        if (cp < 0) return EU_ERR_ARG;       // "Boundary face centroid not on bounding box" (:143-148)
+        canon_pos[i] = cp;
+        partner[i] = -1;
+        side_areas[cp] += area[i];
+        for (int d = 0; d < 3; ++d) cent[3*size_t(i) + d] = centroid[3*size_t(i) + d];
+        cent[3*size_t(i) + cp/2] = 0.0;
+        key[size_t(i)] = cent[3*size_t(i) + (cp/2 + 1)%3] + pi*cent[3*size_t(i) + (cp/2 + 2)%3];
+    }
+    std::vector<int> order(nn);
+    for (int i = 0; i < n; ++i) order[size_t(i)] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key[size_t(a)] < key[size_t(b)]; });
+    std::vector<double> sorted_key(nn);
+    for (int i = 0; i < n; ++i) sorted_key[size_t(i)] = key[size_t(order[size_t(i)])];
+    const double band = (1.0 + pi)*centroid_tol*1.0000001;
+    for (int pos = 0; pos < n; ++pos) {
+        const int i = order[size_t(pos)];
+        if (partner[i] != -1 || !is_periodic[canon_pos[i]]) continue;
+        const int target = canon_pos[i] ^ 1;
+        const size_t lo = size_t(std::lower_bound(sorted_key.begin(), sorted_key.end(), key[size_t(i)] - band) - sorted_key.begin());
+        for (size_t q = lo; q < size_t(n) && sorted_key[q] <= key[size_t(i)] + band; ++q) {
+            const int j = order[q];
+            if (canon_pos[j] != target || partner[j] != -1) continue;
+            if (std::fabs(area[i] - area[j]) > area_tol) continue;
+            double d2 = 0.0;
+            for (int d = 0; d < 3; ++d) { const double v = cent[3*size_t(j) + d] - cent[3*size_t(i) + d]; d2 += v*v; }
+            if (std::sqrt(d2) <= centroid_tol) { partner[i] = j; partner[j] = i; break; }
+        }
+    }
+    return EU_OK;
+}

@@ -122,6 +122,7 @@ def load_library():
     L.eu_cfl_times.argtypes = [C.c_void_p, _dp, _dp]
     L.eu_small_step.argtypes = [C.c_void_p, C.c_double, _dp, C.c_int, _ip, _dp, _dp, _ip, _dp]
     L.eu_compute_cfl_factors.argtypes = [C.POINTER(_Fluid), C.c_int, _dp, _dp, _ip, _dp]
+    L.eu_match_periodic_faces.argtypes = [C.c_int, _dp, _dp, _ip, C.c_double, _ip, _ip, _dp]
     L.eu_compute_residual.argtypes = [C.c_void_p, _dp, _dp, _dp, C.c_int, _ip, _dp, C.c_int, C.c_int, C.c_int, _dp]
     L.eu_compute_cap_pressures.argtypes = [C.c_void_p, _dp, _dp]
     L.eu_cell_velocity.argtypes = [C.c_void_p, _dp]
@@ -210,6 +211,20 @@ def make_fluid(case, cfl_factors=None):
     for k in range(3):
         f.cfl_factor[k] = float(cfl_factors[k])
     return f, keep
+
+
+def match_periodic_faces(centroid, area, is_periodic, spatial_tolerance=1e-6):
+    """findPeriodicPartners / match of the reference (BoundaryPeriodicity.hpp:86-177, .cpp:25-49) on a flat list of
+    boundary faces; host only.  Returns (canon_pos, partner, side_areas)."""
+    cen = np.ascontiguousarray(centroid, dtype=np.float64).reshape(-1, 3)
+    ar = np.ascontiguousarray(area, dtype=np.float64)
+    per = np.ascontiguousarray(is_periodic, dtype=np.int32)
+    n = ar.shape[0]
+    canon, partner, sides = np.zeros(max(n, 1), dtype=np.int32), np.zeros(max(n, 1), dtype=np.int32), np.zeros(6)
+    rc = load_library().eu_match_periodic_faces(n, _d(cen), _d(ar), _i(per), float(spatial_tolerance), _i(canon), _i(partner), _d(sides))
+    if rc != EU_OK:
+        raise EulerB200Error(rc, "boundary face centroid not on the bounding box of all boundary faces")
+    return canon[:n], partner[:n], sides
 
 
 PARAM_KEYS = ("courant_number", "method_viscous", "method_gravity", "method_capillary", "use_cfl_viscous",

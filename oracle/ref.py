@@ -202,6 +202,20 @@ class RefSolver:
         return out
 
 
+def ref_find_periodic_partners(centroid, area, is_periodic, spatial_tolerance=1e-6):
+    """The reference's findPeriodicPartners + match (BoundaryPeriodicity.hpp:86-177, .cpp:25-49) over a mock GridView.
+    Returns (status, canon_pos, partner, side_areas); status 1 = the reference threw."""
+    lib = C.CDLL(REF_LIB)
+    cen = np.ascontiguousarray(centroid, dtype=np.float64).reshape(-1, 3)
+    ar = np.ascontiguousarray(area, dtype=np.float64)
+    per = np.ascontiguousarray(is_periodic, dtype=np.int32)
+    n = ar.shape[0]
+    canon, partner, sides = np.full(max(n, 1), -9, dtype=np.int32), np.full(max(n, 1), -9, dtype=np.int32), np.zeros(6)
+    st = lib.ref_find_periodic_partners(C.c_int(n), _d(cen), _d(ar), _i(per), C.c_double(spatial_tolerance),
+                                        _i(canon), _i(partner), _d(sides))
+    return st, canon[:n], partner[:n], sides
+
+
 # ------------------------------------------------------------------------------------
 # plain-C restatement
 # ------------------------------------------------------------------------------------

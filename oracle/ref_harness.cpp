@@ -15,6 +15,7 @@
 #endif
 #include <opm/porsol/common/BoundaryConditions.hpp>
 #include <opm/porsol/common/SimulatorUtilities.hpp>
+#include <opm/porsol/common/BoundaryPeriodicity.hpp>
 
 #include "FlatGrid.hpp"
 
@@ -218,6 +219,52 @@ namespace {
             os << "\n";
         }
     }
+
+    // Minimal Dune GridView stand-in for findPeriodicPartners (BoundaryPeriodicity.hpp:86-177): one element that owns
+    // all boundary intersections, each with a unique boundary id, a centroid and an area.
+    struct BFaceView {
+        const double* centroid;
+        const double* area;
+        int n;
+        struct Geometry {
+            Dune::FieldVector<double, 3> c;
+            double a;
+            Dune::FieldVector<double, 3> center() const { return c; }
+            double volume() const { return a; }
+        };
+        struct Intersection {
+            const BFaceView* v;
+            int i;
+            int boundaryId() const { return i + 1; }
+            Geometry geometry() const
+            {
+                Geometry g;
+                for (int d = 0; d < 3; ++d) g.c[d] = v->centroid[3*i + d];
+                g.a = v->area[i];
+                return g;
+            }
+        };
+        struct IntersectionIterator {
+            Intersection x;
+            const Intersection* operator->() const { return &x; }
+            IntersectionIterator& operator++() { ++x.i; return *this; }
+            bool operator!=(const IntersectionIterator& o) const { return x.i != o.x.i; }
+        };
+        struct Element {};
+        struct ElementIterator {
+            int pos;
+            Element e;
+            const Element& operator*() const { return e; }
+            ElementIterator& operator++() { ++pos; return *this; }
+            bool operator!=(const ElementIterator& o) const { return pos != o.pos; }
+        };
+        enum { dimension = 3 };
+        template <int codim> struct Codim { typedef ElementIterator Iterator; };
+        template <int codim> ElementIterator begin() const { ElementIterator it; it.pos = 0; return it; }
+        template <int codim> ElementIterator end() const { ElementIterator it; it.pos = 1; return it; }
+        IntersectionIterator ibegin(const Element&) const { IntersectionIterator it; it.x.v = this; it.x.i = 0; return it; }
+        IntersectionIterator iend(const Element&) const { IntersectionIterator it; it.x.v = this; it.x.i = n; return it; }
+    };
 
     GI::Vector vec3(const double* p) { GI::Vector v; v[0] = p[0]; v[1] = p[1]; v[2] = p[2]; return v; }
 
@@ -451,6 +498,34 @@ void ref_cap_pressures(void* hv, const double* sat, double* out)
     std::vector<double> s(sat, sat + N), pc;
     h->capPressures(s, pc);
     std::copy(pc.begin(), pc.end(), out);
+}
+
+// findPeriodicPartners + match (BoundaryPeriodicity.hpp:86-177, .cpp:25-49) on a flat list of boundary faces.
+// Returns 0, or 1 when the reference throws.
+int ref_find_periodic_partners(int n, const double* centroid, const double* area, const int* is_periodic6, double tol,
+                               int* canon_pos, int* partner, double* side_areas6)
+{
+    BFaceView view = { centroid, area, n };
+    std::vector<Opm::BoundaryFaceInfo> info;
+    std::array<double, 6> sa;
+    std::array<bool, 6> per;
+    for (int k = 0; k < 6; ++k) per[k] = is_periodic6[k] != 0;
+    std::ostringstream captured;
+    std::streambuf* old = std::cerr.rdbuf(captured.rdbuf());
+    int status = 0;
+    try {
+        Opm::findPeriodicPartners(info, sa, view, per, tol);
+    } catch (const std::exception&) {
+        status = 1;
+    }
+    std::cerr.rdbuf(old);
+    if (status) return status;
+    for (int k = 0; k < 6; ++k) side_areas6[k] = sa[k];
+    for (size_t q = 0; q < info.size(); ++q) {
+        canon_pos[info[q].face_index] = info[q].canon_pos;
+        partner[info[q].face_index] = info[q].partner_face_index;
+    }
+    return 0;
 }
 
 void ref_cfl_factors(void* hv, double* out3) { static_cast<HarnessBase*>(hv)->cflFactors(out3); }

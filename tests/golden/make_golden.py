@@ -57,5 +57,21 @@ def main():
         print(name, case.N, "cells", out.get("solve_nsteps"))
 
 
+def periodic_matching():
+    """tests/golden/periodic_matching.npz: findPeriodicPartners / match of the reference (BoundaryPeriodicity.hpp:86-177,
+    .cpp:25-49) on the seeded boundary-face lists of tests/test_periodic_matching.py."""
+    from oracle.ref import ref_find_periodic_partners
+    from test_periodic_matching import CASES, FIXTURE, boundary_faces
+    out = {}
+    for k, (dims, per, seed) in enumerate(CASES):
+        cen, area = boundary_faces(*dims, seed=seed)
+        st, canon, partner, sides = ref_find_periodic_partners(cen, area, per)
+        assert st == 0
+        out[f"cen{k}"], out[f"canon{k}"], out[f"partner{k}"], out[f"sides{k}"] = cen, canon, partner, sides
+        print("periodic", dims, per, int((partner >= 0).sum()), "matched of", area.shape[0])
+    np.savez_compressed(FIXTURE, **out)
+
+
 if __name__ == "__main__":
     main()
+    periodic_matching()
