@@ -124,4 +124,4 @@ def test_large_case_scales():
     dt = time.time() - t0
     assert (partner >= 0).all() and np.array_equal(partner[partner], np.arange(area.shape[0]))
     assert np.array_equal(canon[partner], canon ^ 1)
-    assert dt < 5.0, dt
+    assert dt < 30.0, dt              # ~0.3 s here; the reference's fallback scan is quadratic in the unmatched faces
