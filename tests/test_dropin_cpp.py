@@ -19,3 +19,19 @@ def test_dropin_header_matches_reference(tmp_path):
     print(out.stdout)
     print(out.stderr)
     assert out.returncode == 0 and "DROPIN TEST PASSED" in out.stdout, out.stdout + out.stderr
+
+
+def test_dropin_header_fails_loudly_without_a_gpu(tmp_path):
+    """No CPU fallback behind the C++ drop-in either: without a CUDA device initObj throws
+    'EulerUpstream (B200): no CUDA device (there is no CPU fallback)'.  Runs where there is no GPU (the build container)."""
+    if not os.path.exists(BIN):
+        pytest.skip("oracle/_ref/dropin_test not built (needs /root/reference)")
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present: covered by test_dropin_header_matches_reference")
+    except ImportError:
+        pass
+    out = subprocess.run([BIN, str(tmp_path)], capture_output=True, text=True, timeout=120)
+    assert out.returncode != 0
+    assert "no CUDA device (there is no CPU fallback)" in out.stderr and "DROPIN TEST PASSED" not in out.stdout
