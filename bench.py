@@ -170,7 +170,7 @@ def run_cpu(a, synth):
     value = case.N*a.cpu_substeps/secs
     sample = (f"{dims[0]}x{dims[1]}x{dims[2]} slab of the same workload ({case.N} cells) x {a.cpu_substeps} substeps, "
               f"{secs:.2f} s in the substep loop, 1 thread (the reference is serial)")
-    return {"value": value, "unit": "cell-substeps/s", "cores": 1, "kind": kind, "sample": sample}
+    return {"value": value, "unit": "cell-substeps/s", "cores": 1, "kind": kind, "sample": sample, "seconds": secs}
 
 
 def main():
@@ -190,8 +190,11 @@ def main():
             if time.time() - t0 > 120:
                 break
         best = max(vals, key=lambda v: v["value"])
+        ms = 1e3*best.pop("seconds")
+        for v in vals:
+            v.pop("seconds", None)
         line = {"impl": "reference", "metric": "EulerUpstream cell-substeps/s", "value": best["value"], "unit": "cell-substeps/s",
-                "n_gpus": a.gpus, "steps": len(vals), "warmup": 0, "ms_per_step": None, "higher_is_better": True,
+                "n_gpus": a.gpus, "steps": len(vals), "warmup": 0, "ms_per_step": ms, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload_name(a), "substeps_per_step": a.cpu_substeps, "sample": best["sample"]},
                 "cpu_baseline": best,
@@ -337,6 +340,7 @@ def main():
                            "ms_per_step": 1e3*e2e_wall/a.steps}
         if not a.no_cpu:
             line["cpu_baseline"] = run_cpu(a, synth)
+            line["cpu_baseline"].pop("seconds", None)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
