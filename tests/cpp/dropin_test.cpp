@@ -6,148 +6,7 @@
 // BasicBoundaryConditions<true,true> objects, driven with identical inputs, and compared.
 // Built here by oracle/Makefile into oracle/_ref/dropin_test (needs /root/reference); run on the GPU box
 // by tests/test_dropin_cpp.py.
-#define EULER_B200_KEEP_REFERENCE
-#include <opm/porsol/euler/EulerUpstream.hpp>                       // the reference (first on the include path)
-#include <opm/porsol/common/ReservoirPropertyCapillary.hpp>
-#include <opm/porsol/common/ReservoirPropertyCapillaryAnisotropicRelperm.hpp>
-#include <opm/porsol/common/BoundaryConditions.hpp>
-#include <opm/porsol/common/SimulatorUtilities.hpp>                  // the reference's post-transport loops
-#include "../../opm-porsol_b200/host/opm/porsol/euler/EulerUpstream.hpp"   // the drop-in
-#include "../../opm-porsol_b200/host/opm/porsol/euler/EulerUpstreamResidual.hpp"
-#include "../../opm-porsol_b200/host/opm/porsol/euler/b200/Diagnostics.hpp"
-#include "../../oracle/FlatGrid.hpp"
-
-#include <cmath>
-#include <cstdio>
-#include <cstdlib>
-#include <fstream>
-#include <iomanip>
-#include <memory>
-#include <string>
-
-typedef flatgrid::Grid GI;
-typedef Opm::BasicBoundaryConditions<true, true> BCs;
-
-struct Rng {
-    unsigned long long s;
-    explicit Rng(unsigned long long seed) : s(seed) {}
-    double next() { s = s*6364136223846793005ULL + 1442695040888963407ULL; return double(s >> 11)*(1.0/9007199254740992.0); }
-};
-
-// half-face fluxes by face iterator only (the attic TestSolution pattern, EulerSolverTester.hpp:100-103)
-struct IterFlux {
-    std::vector<double> v;
-    double outflux(const GI::CellIterator::FaceIterator& f) const { return v[f->halfFaceIndex()]; }
-};
-// ... and with the flat accessor of IncompFlowSolverHybrid::FlowSolution (:430-433)
-struct FlatFlux : IterFlux {
-    using IterFlux::outflux;
-    double outflux(int hf) const { return v[hf]; }
-};
-
-static void buildGrid(GI& grid, BCs& bc, int nx, int ny, int nz, Rng& rng, bool periodic_x)
-{
-    flatgrid::Data& d = grid.data();
-    const int N = nx*ny*nz;
-    d.num_cells = N;
-    d.hf_offset.resize(N + 1);
-    const double h[3] = { 1.0, 0.8, 0.5 };
-    int nbid = 0;
-    std::vector<int> lo_bid(ny*nz, 0), hi_bid(ny*nz, 0);
-    for (int c = 0; c < N; ++c) {
-        const int i = c % nx, j = (c/nx) % ny, k = c/(nx*ny);
-        const int ijk[3] = { i, j, k }, ext[3] = { nx, ny, nz }, stride[3] = { 1, nx, nx*ny };
-        d.hf_offset[c] = 6*c;
-        d.cell_volume.push_back(h[0]*h[1]*h[2]*(0.9 + 0.2*rng.next()));
-        for (int a = 0; a < 3; ++a) d.cell_centroid.push_back((ijk[a] + 0.5)*h[a] + 0.02*(rng.next() - 0.5));
-        for (int a = 0; a < 3; ++a) {
-            for (int s = 0; s < 2; ++s) {
-                const bool bnd = s == 0 ? ijk[a] == 0 : ijk[a] == ext[a] - 1;
-                d.hf_neighbour.push_back(bnd ? -1 : c + (s ? stride[a] : -stride[a]));
-                int bid = 0;
-                if (bnd) {
-                    bid = ++nbid;
-                    if (a == 0) (s == 0 ? lo_bid : hi_bid)[j + ny*k] = bid;
-                }
-                d.hf_bid.push_back(bid);
-                d.hf_area.push_back(h[(a + 1) % 3]*h[(a + 2) % 3]);
-                for (int q = 0; q < 3; ++q) d.hf_normal.push_back(q == a ? (s ? 1.0 : -1.0) : 0.0);
-                for (int q = 0; q < 3; ++q) {
-                    double x = (ijk[q] + 0.5)*h[q];
-                    if (q == a) x = (ijk[q] + s)*h[q];
-                    d.hf_centroid.push_back(x);
-                }
-            }
-        }
-    }
-    d.hf_offset[N] = 6*N;
-    bc.resize(nbid + 1);
-    for (int b = 1; b <= nbid; ++b) bc.satCond(b) = Opm::SatBC(Opm::SatBC::Dirichlet, rng.next());
-    if (periodic_x) {
-        for (int m = 0; m < ny*nz; ++m) {
-            bc.satCond(lo_bid[m]) = Opm::SatBC(Opm::SatBC::Periodic, 0.0);
-            bc.satCond(hi_bid[m]) = Opm::SatBC(Opm::SatBC::Periodic, 0.0);
-            bc.setPeriodicPartners(lo_bid[m], hi_bid[m]);
-        }
-    }
-}
-
-static std::string writeRocks(const std::string& dir, int n_rocks, bool aniso)
-{
-    const std::string list = dir + "/rocklist.txt";
-    std::ofstream rl(list.c_str());
-    rl << n_rocks << "\n";
-    for (int r = 0; r < n_rocks; ++r) {
-        const int n = 9 + 4*r;
-        const double swir = 0.05 + 0.04*r, sor = 0.1;
-        for (int ph = 0; ph < (aniso ? 2 : 1); ++ph) {
-            const std::string fn = "rock" + std::to_string(r) + (aniso ? (ph ? "_o" : "_w") : "") + ".txt";
-            std::ofstream os((dir + "/" + fn).c_str());
-            os << "# generated by tests/cpp/dropin_test.cpp\n" << std::setprecision(17);
-            for (int i = 0; i < n + 2; ++i) {
-                double s = i == 0 ? 0.0 : (i == n + 1 ? 1.0 : swir + (1.0 - swir - sor)*(i - 1)/(n - 1));
-                double se = std::min(1.0, std::max(0.0, (s - swir)/(1.0 - swir - sor)));
-                double krw = se*se, kro = (1 - se)*(1 - se), J = (0.2 + 0.1*r)*(1 - se)/std::sqrt(std::max(se, 0.03));
-                if (aniso) {
-                    const double kr = ph == 0 ? krw : kro;
-                    os << J*2.0e4 << " " << s << " " << kr << " " << 0.8*kr << " " << 0.5*kr << "\n";
-                } else {
-                    os << s << " " << krw << " " << kro << " " << J << "\n";
-                }
-            }
-            rl << fn << (aniso && ph == 0 ? " " : "\n");
-        }
-    }
-    return list;
-}
-
-template <class RP>
-static void initProps(RP& rp, int N, Rng& rng, int n_rocks, const std::string& dir, bool aniso)
-{
-    std::shared_ptr<Opm::Deck> deck(new Opm::Deck);
-    deck->dims_[0] = N; deck->dims_[1] = 1; deck->dims_[2] = 1;
-    std::vector<int> gc(N), satnum(N);
-    std::vector<double> poro(N), k[6];
-    for (int m = 0; m < 6; ++m) k[m].resize(N);
-    for (int c = 0; c < N; ++c) {
-        gc[c] = c;
-        satnum[c] = 1 + int(rng.next()*n_rocks) % std::max(n_rocks, 1);
-        poro[c] = 0.1 + 0.2*rng.next();
-        const double base = 1e-13*(0.5 + rng.next());
-        k[0][c] = base; k[1][c] = 0.7*base; k[2][c] = 0.2*base;                 // xx yy zz
-        k[3][c] = 0.1*base*(rng.next() - 0.5); k[4][c] = 0.1*base*(rng.next() - 0.5); k[5][c] = 0.05*base*(rng.next() - 0.5);
-    }
-    deck->setDouble("PORO", poro);
-    deck->setDouble("PERMX", k[0]); deck->setDouble("PERMY", k[1]); deck->setDouble("PERMZ", k[2]);
-    deck->setDouble("PERMXY", k[3]); deck->setDouble("PERMXZ", k[4]); deck->setDouble("PERMYZ", k[5]);
-    if (n_rocks > 0) deck->setInt("SATNUM", satnum);
-    std::string list;
-    if (n_rocks > 0) list = writeRocks(dir, n_rocks, aniso);
-    std::streambuf* old = std::cout.rdbuf(0);
-    rp.init(deck, gc, 0.0, n_rocks > 0 ? &list : 0, !aniso, 0.03, 0.3);
-    std::cout.rdbuf(old);
-    std::cout.clear();
-}
+#include "fixtures.hpp"
 
 template <class RP, class Flux>
 static int runCase(const char* name, int nx, int ny, int nz, int n_rocks, bool aniso, bool periodic_x, int mode,

@@ -35,3 +35,17 @@ def test_dropin_header_fails_loudly_without_a_gpu(tmp_path):
     out = subprocess.run([BIN, str(tmp_path)], capture_output=True, text=True, timeout=120)
     assert out.returncode != 0
     assert "no CUDA device (there is no CPU fallback)" in out.stderr and "DROPIN TEST PASSED" not in out.stdout
+
+
+FLATTEN = os.path.join(ROOT, "oracle", "_ref", "flatten_test")
+
+
+def test_dropin_headers_host_logic_against_recording_stub(tmp_path):
+    """tests/cpp/flatten_test.cpp: the drop-in headers linked against a recording stub of the C ABI (no GPU): the
+    flattening walk, fluid extraction, parameter keys, flux gathering, exception mapping, the residual mirror and the
+    diagnostics wrappers, against what the reference's own grid / property / boundary-condition objects say."""
+    if not os.path.exists(FLATTEN):
+        pytest.skip("oracle/_ref/flatten_test not built (needs /root/reference)")
+    out = subprocess.run([FLATTEN, str(tmp_path)], capture_output=True, text=True, timeout=300)
+    print(out.stdout)
+    assert out.returncode == 0 and "FLATTEN TEST PASSED" in out.stdout, out.stdout + out.stderr
