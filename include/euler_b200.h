@@ -191,11 +191,13 @@ int eu_transport_solve(eu_handle h, double* saturation, double time, const doubl
  * at a fraction of the link rate.  Two remedies, both optional:
  *  - eu_host_alloc / eu_host_free: page-locked host memory for the caller's flat flux array (the drop-in C++ header
  *    gathers pressure_sol.outflux(f) into such a buffer);
- *  - buffers of >= 1 MiB passed to eu_transport_solve / eu_upload_state / eu_upload_saturation / eu_download_saturation /
- *    eu_compute_residual that are not page-locked yet are registered with the driver on first use and stay registered
- *    while the same (pointer, size) keeps coming (an IMPES loop passes the same vectors every step); at most 4
- *    registrations per solver, released by eu_destroy or eu_host_unpin_all.  Set EU_PIN_CACHE=0 to turn this off
- *    (e.g. when the application frees and reallocates its vectors between calls). */
+ *  - opt-in, EU_PIN_CACHE=1 in the environment: buffers of >= 1 MiB passed to eu_transport_solve / eu_upload_state /
+ *    eu_upload_saturation / eu_download_saturation / eu_compute_residual that are not page-locked yet are registered
+ *    with the driver on first use and stay registered while the same (pointer, size) keeps coming (an IMPES loop
+ *    passes the same vectors every step); at most 4 registrations per solver, released by eu_destroy or
+ *    eu_host_unpin_all.  It is off by default because a registered buffer must not be freed or reallocated while the
+ *    registration lives (the driver would keep transferring from the old pages): enable it only when the application
+ *    keeps its vectors for the lifetime of the solver, or calls eu_host_unpin_all before releasing them. */
 void* eu_host_alloc(unsigned long long bytes);
 void eu_host_free(void* p);
 void eu_host_unpin_all(eu_handle h);

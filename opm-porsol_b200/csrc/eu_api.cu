@@ -121,7 +121,7 @@ struct eu_solver {
     struct Pinned { const void* p; size_t bytes; unsigned long long stamp; };
     std::vector<Pinned> pinned;
     unsigned long long pin_clock = 0;
-    bool pin_cache = true;
+    bool pin_cache = false;            // opt-in (EU_PIN_CACHE=1): the caller must not free a registered buffer while the solver lives
     DevBuf<unsigned long long> d_fail_key;
     DevBuf<int> d_src_cell;
     DevBuf<double> d_src_rate;
