@@ -87,3 +87,27 @@ def test_cuda_reproduces_golden(name, case, mode):
         else:
             assert np.abs(sat - g["solve_sat"]).max() <= 1e-9
     dev.close()
+
+
+def test_survey_known_answer():
+    """The known-answer case SURVEY 8c records from a separate probe of the unmodified reference headers (mock Cartesian
+    10x10x10, dx = 0.1, K = diag(1e-13, 1e-13, 1e-14), phi = 0.2, no rocks, default Dirichlet S = 1 boundaries,
+    v = (1e-6, 0, 0), g = (0, 0, -9.81), S0 = 0, CFL factors (0.3, 2e-4, 5e7), transportSolve(86400 s), defaults):
+    CFL times 6000 / 227537 / 500 s, 346 substeps, sum S = 414.11235818963286, S[0], S[999] as below."""
+    from opm_porsol_b200 import synth
+    from oracle.ref import PortSolver
+    g = synth.cartesian_grid(10, 10, 10, 0.1, 0.1, 0.1, unique_bids=False)
+    N = g["N"]
+    perm = np.zeros((N, 9))
+    perm[:, 0] = perm[:, 4] = 1e-13
+    perm[:, 8] = 1e-14
+    case = synth.make_case("survey-kat", g, poro=np.full(N, 0.2), perm=perm, sat0=np.zeros(N), gravity=[0.0, 0.0, -9.81],
+                           hf_flux=synth.constant_velocity_flux(g, (1e-6, 0.0, 0.0)), time=86400.0)
+    port = PortSolver(case, cfl_factors=[0.3, 2e-4, 5e7])
+    cfl = port.cfl_times()
+    assert cfl[0] == 6000.0 and cfl[2] == 500.0 and abs(cfl[1] - 227537.0) < 1.0
+    out = port.transport_solve(case.sat0, time=86400.0)
+    s = out["sat"]
+    assert out["nsteps"] == 346 and out["attempts"] == 1
+    assert float(s.sum()) == 414.11235818963286
+    assert float(s[0]) == 0.53870412522172473 and float(s[999]) == 0.30118148462420075
