@@ -105,7 +105,7 @@ def test_survey_known_answer():
                            hf_flux=synth.constant_velocity_flux(g, (1e-6, 0.0, 0.0)), time=86400.0)
     port = PortSolver(case, cfl_factors=[0.3, 2e-4, 5e7])
     cfl = port.cfl_times()
-    assert cfl[0] == 6000.0 and cfl[2] == 500.0 and abs(cfl[1] - 227537.0) < 1.0
+    assert abs(cfl[0] - 6000.0) < 1e-6 and abs(cfl[2] - 500.0) < 1e-6 and abs(cfl[1] - 227537.0) < 1.0   # as printed in the survey
     out = port.transport_solve(case.sat0, time=86400.0)
     s = out["sat"]
     assert out["nsteps"] == 346 and out["attempts"] == 1
