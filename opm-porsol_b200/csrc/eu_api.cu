@@ -504,6 +504,55 @@ int build_items(eu_handle h, int lo, int hi)
         const char* e = getenv("EU_MARCH_LEN");
         if (e && atoi(e) > 0) {
             lmax = std::min(atoi(e), 4096);
+        } else if (getenv("EU_ITEM_RULE") && std::strcmp(getenv("EU_ITEM_RULE"), "sim") == 0) {
+            // EXPERIMENT (opt-in, unmeasured): pick L by simulating the round-robin hand-out exactly -- piece lengths in
+            // list order, load of a warp = sum over its items of (length + EU_ITEM_HEAD steps) -- and minimising the
+            // busiest warp's load (tools/item_balance.py is the same model).  Any rank count.
+            std::vector<int> chain_n;
+            std::vector<char> seen(cls.size(), 0);
+            long long singles = 0;
+            for (int s = lo; s < hi; ++s) {
+                if (seen[size_t(s - lo)]) continue;
+                const int id = cls[size_t(s - lo)];
+                if (id == EU_ITEM_GENERIC) { ++singles; continue; }
+                const int n = chain_length(s, id, seen);
+                const int step = std::max(classes[size_t(id)].D/EU_SLICE, 1);
+                for (int k = 0; k < n; ++k) seen[size_t(s + k*step - lo)] = 1;
+                chain_n.push_back(n);
+            }
+            const char* eh = getenv("EU_ITEM_HEAD");
+            const double head = eh ? atof(eh) : 1.0;
+            double best = 1e300;
+            std::vector<double> load(size_t(n_warps), 0.0);
+            for (int L = 4; L <= 48; ++L) {
+                // pieces of all chains, plane group by plane group (the order of the scan below): the k-th piece of
+                // every chain, then the (k+1)-th
+                std::fill(load.begin(), load.end(), 0.0);
+                long long v = 0;
+                for (long long q = 0; q < singles; ++q, ++v) load[size_t(v % n_warps)] += 1.0 + head;
+                std::map<int, std::vector<int> > pieces_of;          // chain length -> piece lengths (few distinct lengths)
+                size_t max_pieces = 0;
+                for (int n : chain_n) {
+                    std::vector<int>& pl = pieces_of[n];
+                    if (pl.empty()) {
+                        for (int left = n; left > 0;) {
+                            const int pcs = (left + L - 1)/L;
+                            const int len = (left + pcs - 1)/pcs;
+                            pl.push_back(len);
+                            left -= len;
+                        }
+                    }
+                    max_pieces = std::max(max_pieces, pl.size());
+                }
+                for (size_t k = 0; k < max_pieces; ++k) {
+                    for (int n : chain_n) {
+                        const std::vector<int>& pl = pieces_of[n];
+                        if (k < pl.size()) { load[size_t(v % n_warps)] += pl[k] + head; ++v; }
+                    }
+                }
+                const double mx = *std::max_element(load.begin(), load.end());
+                if (mx < best) { best = mx; lmax = L; }
+            }
         } else if (h->cfg.world_size > 1) {
             while (lmax > 2 && (hi - lo)/lmax < 6*n_warps) lmax /= 2;
         } else {

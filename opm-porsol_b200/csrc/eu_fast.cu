@@ -29,6 +29,10 @@ constexpr bool kStoredLam = true;
 constexpr bool kStoredLam = false;
 #endif
 
+#ifdef EU_DYNAMIC_ITEMS
+__device__ unsigned g_item_counter;          // experiment: next unassigned work item of the running launch
+#endif
+
 constexpr int kWarpsPerBlock = 8;
 constexpr int kBlock = kWarpsPerBlock*32;
 
@@ -733,6 +737,26 @@ __global__ void __launch_bounds__(kBlock, MINB) k_fast_step(EuGridDev g, EuTable
     int vi = v - nAB;
     if (vi >= f.n_items) return;
     int2 item = __ldg(f.items + vi);
+#ifdef EU_DYNAMIC_ITEMS
+    // EXPERIMENT (not the default build, unmeasured): after its first item -- assigned statically, so that the warps of
+    // a block still start on neighbouring grid rows -- a warp takes the next unassigned item from a per-launch counter
+    // instead of item vi + #warps: no warp idles while items are left.  The host zeroes the counter before the launch.
+    for (;;) {
+        const int cls = int(unsigned(item.y) >> 16);
+        if (TENSOR || cls == EU_ITEM_GENERIC) {
+            slice_generic<ROCKS, MULTIROCK, CAP, NN, B6, B8, TENSOR>(L, g, t, f, a, halo, item.x, -1, lane, slice_lo);
+        } else {
+            const EuSliceClass* cl = classes + cls;
+            if (cl->rec_mask != 0) march_item_records<ROCKS, MULTIROCK, CAP, NN>(L, g, t, f, a, cl, item.x, item.y & 0xffff, lane);
+            else                   march_item_impl<ROCKS, MULTIROCK, CAP, NN, false>(L, g, t, f, a, cl, item.x, item.y & 0xffff, lane);
+        }
+        int next = 0;
+        if (lane == 0) next = n_warps + int(atomicAdd(&g_item_counter, 1u));
+        next = __shfl_sync(0xffffffffu, next, 0);
+        if (next >= f.n_items) break;
+        item = __ldg(f.items + next);
+    }
+#else
     for (;;) {
         // the next item of this warp is fetched before the current one is processed
         const bool has_next = vi + n_warps < f.n_items;
@@ -750,6 +774,7 @@ __global__ void __launch_bounds__(kBlock, MINB) k_fast_step(EuGridDev g, EuTable
         item = item_next;
         vi += n_warps;
     }
+#endif
 }
 
 // ---- diagonal tensor mobility on general (oblique) face normals ---------------------------------------------
@@ -937,6 +962,13 @@ static void launch_variant(const EuGridDev& g, const EuTablesDev& t, const EuFas
     const int need = (n + kWarpsPerBlock - 1)/kWarpsPerBlock;
     if (blocks > need) blocks = need;
     if (blocks < 1) return;
+#ifdef EU_DYNAMIC_ITEMS
+    {
+        void* counter = nullptr;
+        cudaGetSymbolAddress(&counter, g_item_counter);
+        cudaMemsetAsync(counter, 0, sizeof(unsigned), st);
+    }
+#endif
     kern<<<blocks, kBlock, smem, st>>>(g, t, f, a, halo, slice_lo, slice_hi, (int)smem_tables);
 }
 
