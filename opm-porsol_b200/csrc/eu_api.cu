@@ -489,8 +489,8 @@ int build_items(eu_handle h, int lo, int hi)
     // chain is cut into ceil(n/L) pieces of nearly equal length.  A fixed L = 32 left 8 % of the warps' time idle on a
     // 128-plane slab (9.2 items per warp -> 10).  EU_MARCH_LEN overrides L.  Measured (profiles/README.md): +5-7 % on
     // single-rank grids of 32-128 planes, neutral at 256; on a 2-rank run the long pieces this rule picks there (63
-    // steps) were 10 % slower than L = 32, so decomposed runs keep the fixed rule (L = 32, halved while a warp would
-    // get fewer than 6 items) until that is understood.
+    // steps) were 10 % slower than L = 32 -- plausibly because the warps of a block drift apart in z over a long march and
+    // stop sharing their neighbours' lines in L1 -- so decomposed runs use the exact simulation below with short pieces.
     const int n_warps = h->n_sms*32;
     auto chain_length = [&](int s, int id, const std::vector<char>& taken) {
         int n = 1;
@@ -501,13 +501,22 @@ int build_items(eu_handle h, int lo, int hi)
     };
     int lmax = 32;
     {
+        // EU_ITEM_RULE = fixed | sim | auto overrides the choice below (tuning knob)
+        const char* rule = getenv("EU_ITEM_RULE");
+        const bool rule_fixed = rule && std::strcmp(rule, "fixed") == 0;
+        const bool rule_sim = rule ? std::strcmp(rule, "sim") == 0 : h->cfg.world_size > 1;
         const char* e = getenv("EU_MARCH_LEN");
         if (e && atoi(e) > 0) {
             lmax = std::min(atoi(e), 4096);
-        } else if (getenv("EU_ITEM_RULE") && std::strcmp(getenv("EU_ITEM_RULE"), "sim") == 0) {
-            // EXPERIMENT (opt-in, unmeasured): pick L by simulating the round-robin hand-out exactly -- piece lengths in
-            // list order, load of a warp = sum over its items of (length + EU_ITEM_HEAD steps) -- and minimising the
-            // busiest warp's load (tools/item_balance.py is the same model).  Any rank count.
+        } else if (rule_fixed) {
+            while (lmax > 2 && (hi - lo)/lmax < 6*n_warps) lmax /= 2;
+        } else if (rule_sim) {
+            // L by simulating the round-robin hand-out exactly -- piece lengths in list order, load of a warp = sum over
+            // its items of (length + head steps) -- and minimising the busiest warp's load (tools/item_balance.py is
+            // the same model).  The rule of decomposed runs, restricted there to short pieces (6..16 steps): the fixed
+            // rule leaves 8 % of the warps' time idle on 2, 4 and 8 ranks of the bench grid (8192 column slices over
+            // 3552 warps), pieces of 10-14 steps 1-2 %; short pieces measured +5 % on a single-rank 32-plane slab, long
+            // ones (63 steps) -10 % on 2 ranks.  EU_ITEM_RULE=sim applies it to any run with L = 4..48.
             std::vector<int> chain_n;
             std::vector<char> seen(cls.size(), 0);
             long long singles = 0;
@@ -521,10 +530,13 @@ int build_items(eu_handle h, int lo, int hi)
                 chain_n.push_back(n);
             }
             const char* eh = getenv("EU_ITEM_HEAD");
-            const double head = eh ? atof(eh) : 1.0;
+            const double head = eh ? atof(eh) : 0.5;
+            const int L_lo = rule ? 4 : 6, L_hi = rule ? 48 : 16;
             double best = 1e300;
+            // the warps the persistent grid really has (3 blocks of 8 per SM, 2 with the capillary term)
+            const int n_warps = h->n_sms*eu_fast_warps_per_sm(h->par.method_capillary != 0);
             std::vector<double> load(size_t(n_warps), 0.0);
-            for (int L = 4; L <= 48; ++L) {
+            for (int L = L_lo; L <= L_hi; ++L) {
                 // pieces of all chains, plane group by plane group (the order of the scan below): the k-th piece of
                 // every chain, then the (k+1)-th
                 std::fill(load.begin(), load.end(), 0.0);
@@ -553,8 +565,6 @@ int build_items(eu_handle h, int lo, int hi)
                 const double mx = *std::max_element(load.begin(), load.end());
                 if (mx < best) { best = mx; lmax = L; }
             }
-        } else if (h->cfg.world_size > 1) {
-            while (lmax > 2 && (hi - lo)/lmax < 6*n_warps) lmax /= 2;
         } else {
             // chain lengths (a dry run of the scan below with unlimited pieces)
             std::vector<int> chain_n;

@@ -983,6 +983,14 @@ static int fast_variant()
     return v;
 }
 
+// resident warps per SM of the variant launch_fast picks (8 warps per block): what the host's work-item model needs
+int eu_fast_warps_per_sm(bool capillary)
+{
+    int v = fast_variant();
+    if (v == 0) v = capillary ? 1 : 3;
+    return kWarpsPerBlock*(v == 1 ? 2 : (v == 2 ? 4 : 3));
+}
+
 template <bool ROCKS, bool MULTIROCK, bool CAP, bool NN>
 static void launch_fast(const EuGridDev& g, const EuTablesDev& t, const EuFastDev& f, const EuStepArgs& a,
                         const EuHaloDev& halo, int slice_lo, int slice_hi, int n_sms, size_t smem, cudaStream_t st)

@@ -224,6 +224,7 @@ void eu_launch_fast_step_t3(const EuGridDev& g, const EuTablesDev& t, const EuFa
                             int slice_lo, int slice_hi, int n_sms, cudaStream_t st);
 void eu_launch_ghost_adjacent(const EuGridDev& g, int* out4, cudaStream_t st);
 size_t eu_fast_smem_bytes(const EuTablesDev& t);
+int eu_fast_warps_per_sm(bool capillary);   // resident warps per SM of the substep kernel variant in use
 bool eu_fast_uses_stored_lam();      // build-time choice of eu_fast.cu: per-cell mobility pairs kept in HBM
 
 #endif

@@ -84,9 +84,18 @@ def main():
     chain = interior - singles
     print(f"{columns} column slices, {interior} interior planes (chain {chain} + {singles} single-step planes), "
           f"{boundary_planes} halo planes, {n_warps} warps")
-    rules = {"fixed": fixed_rule(columns*interior, n_warps), "auto(<=64)": auto_rule(columns, chain, singles, n_warps)}
+    def sim_rule(lo, hi, head):
+        best, bestL = 1e300, lo
+        for L in range(lo, hi + 1):
+            mx, _ = makespan(items_for(columns, chain, singles, L), n_warps, head)
+            if mx < best:
+                best, bestL = mx, L
+        return bestL
+    rules = {"fixed": fixed_rule(columns*interior, n_warps), "auto(<=64)": auto_rule(columns, chain, singles, n_warps),
+             "sim(6..16, head 0.5: decomposed runs)": sim_rule(6, 16, 0.5)}
     print(f"rules: {rules}")
     print(f"{'L':>4} {'items':>8} {'items/warp':>10} {'max load':>9} {'mean':>8} {'imbalance':>9}")
+    print("(eu_api.cu evaluates the auto rule with 32 warps per SM, as measured; fixed and sim as shown here)")
     for L in sorted(set(list(range(4, 65, 2)) + list(rules.values()))):
         lens = items_for(columns, chain, singles, L)
         mx, mean = makespan(lens, n_warps, a.head)
