@@ -530,13 +530,15 @@ int build_items(eu_handle h, int lo, int hi)
                 chain_n.push_back(n);
             }
             const char* eh = getenv("EU_ITEM_HEAD");
-            const double head = eh ? atof(eh) : 0.5;
+            // start of a march in steps: two pieces of 15 beat four of 8 by 5 % at equal balance on a 32-plane slab -> ~0.75
+            const double head = eh ? atof(eh) : 0.75;
             const int L_lo = rule ? 4 : 6, L_hi = rule ? 48 : 16;
             double best = 1e300;
             // the warps the persistent grid really has (3 blocks of 8 per SM, 2 with the capillary term)
             const int n_warps = h->n_sms*eu_fast_warps_per_sm(h->par.method_capillary != 0);
             std::vector<double> load(size_t(n_warps), 0.0);
-            for (int L = L_lo; L <= L_hi; ++L) {
+            // busiest warp's load for piece length L
+            auto simulate = [&](int L) {
                 // pieces of all chains, plane group by plane group (the order of the scan below): the k-th piece of
                 // every chain, then the (k+1)-th
                 std::fill(load.begin(), load.end(), 0.0);
@@ -562,8 +564,18 @@ int build_items(eu_handle h, int lo, int hi)
                         if (k < pl.size()) { load[size_t(v % n_warps)] += pl[k] + head; ++v; }
                     }
                 }
-                const double mx = *std::max_element(load.begin(), load.end());
+                return *std::max_element(load.begin(), load.end());
+            };
+            for (int L = L_lo; L <= L_hi; ++L) {
+                const double mx = simulate(L);
                 if (mx < best) { best = mx; lmax = L; }
+            }
+            if (!rule) {
+                // Decomposed runs leave the fixed rule (the one measured at 2 and 8 GPUs) only where the model promises
+                // at least 4 %: a shorter piece also means more march heads, whose real cost the model only estimates.
+                int lfixed = 32;
+                while (lfixed > 2 && (hi - lo)/lfixed < 6*(h->n_sms*32)) lfixed /= 2;
+                if (best > 0.96*simulate(lfixed)) lmax = lfixed;
             }
         } else {
             // chain lengths (a dry run of the scan below with unlimited pieces)

@@ -92,7 +92,7 @@ def main():
                 best, bestL = mx, L
         return bestL
     rules = {"fixed": fixed_rule(columns*interior, n_warps), "auto(<=64)": auto_rule(columns, chain, singles, n_warps),
-             "sim(6..16, head 0.5: decomposed runs)": sim_rule(6, 16, 0.5)}
+             "sim(6..16, head 0.75: decomposed runs, if >= 4 % better than fixed)": sim_rule(6, 16, 0.75)}
     print(f"rules: {rules}")
     print(f"{'L':>4} {'items':>8} {'items/warp':>10} {'max load':>9} {'mean':>8} {'imbalance':>9}")
     print("(eu_api.cu evaluates the auto rule with 32 warps per SM, as measured; fixed and sim as shown here)")
