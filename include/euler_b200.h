@@ -53,8 +53,10 @@ enum { EU_MOB_SCALAR = 0, EU_MOB_DIAGONAL = 1 };
 
 /* arithmetic modes */
 enum {
-    EU_MODE_AUTO = 0,    /* fast where implemented (scalar mobility; diagonal tensor mobility on grids whose face
-                            normals are axis-aligned), strict otherwise */
+    EU_MODE_AUTO = 0,    /* fast wherever the FAST tables apply: scalar mobility, and the diagonal tensor mobility class on
+                            any grid (axis-aligned normals: scalar formula per face axis; oblique normals: the
+                            three-component kernel); strict only when the rock tables do not fit the FAST search
+                            (nodes closer than 1/4096, more than 48 curve sets) */
     EU_MODE_STRICT = 1,  /* reference operation order, no FMA contraction: bit-identical to the reference */
     EU_MODE_FAST = 2     /* static per-face quantities pre-contracted to scalars, FMA allowed:
                             |dS| error ~1e-16 per substep (gate: 1e-12), identical step counts */
@@ -172,10 +174,16 @@ int eu_grid_end(eu_handle h);               /* builds the device structures */
 int eu_local_cells(eu_handle h);
 long long eu_local_halffaces(eu_handle h);
 /* the arithmetic mode in effect after eu_grid_end: EU_MODE_STRICT or EU_MODE_FAST (EU_MODE_AUTO resolves to FAST for
- * the scalar mobility class and for the diagonal tensor class on grids with axis-aligned face normals, else STRICT) */
+ * both mobility classes on any grid -- the tensor class on oblique normals runs the three-component FAST kernel, NOT
+ * STRICT -- and to STRICT only when the rock tables do not fit the FAST interval search) */
 int eu_resolved_mode(eu_handle h);
 /* fraction of (slice, slot) pairs whose adjacency is described by an 8-byte descriptor instead of 32 records */
 double eu_regular_fraction(eu_handle h);
+/* the work plan of the FAST substep kernel, as built by the last substep / transportSolve (zeros before that and in
+ * STRICT mode): out[0] = fraction of the own slices (32 cells) that belong to a slice class, out[1] = number of work
+ * items, out[2] = longest march (slices per item), out[3] = mean march length over the class items.  Tests use it
+ * to assert which code path a parity case exercised. */
+int eu_work_plan(eu_handle h, double out[4]);
 
 /* ---- EulerUpstream::transportSolve (EulerUpstream_impl.hpp:151-218) -------------------
  * saturation:  local cells (in/out; ghost entries are inputs only)

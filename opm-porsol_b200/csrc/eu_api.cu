@@ -100,8 +100,10 @@ struct eu_solver {
     std::vector<int> h_slice_base;
     DevBuf<int2> d_items;
     DevBuf<EuSliceClass> d_classes;
-    int n_items = 0, n_classes = 0, items_lo = -1, items_hi = -1;
+    int n_items = 0, n_classes = 0, items_lo = -1, items_hi = -1, items_variant = -1;
     double class_fraction = 0.0;       // share of the own slices that belong to a slice class
+    int plan_max_len = 0;
+    double plan_mean_len = 0.0;
     DevBuf<double> d_porevol, d_inv_porevol, d_pcscale, d_T, d_nn;
     DevBuf<double2> d_lam[2];          // per cell {lambda_w, lambda_o} of the state in d_S[k] (FAST)
     DevBuf<double2> d_qg;              // per unique face {flux of the current transportSolve, G}
@@ -400,7 +402,9 @@ struct ClassKey {
 
 int build_items(eu_handle h, int lo, int hi)
 {
-    if (h->items_lo == lo && h->items_hi == hi) return EU_OK;
+    // the plan depends on the slice range and on the kernel variant (resident warps per SM differ with the capillary term)
+    const int variant_key = h->par.method_capillary != 0;
+    if (h->items_lo == lo && h->items_hi == hi && h->items_variant == variant_key) return EU_OK;
     const std::vector<int>& base = h->h_slice_base;
     const size_t n_desc = size_t(base.back()/EU_SLICE);
     std::vector<int2> desc(n_desc + 1);
@@ -503,8 +507,11 @@ int build_items(eu_handle h, int lo, int hi)
     {
         // EU_ITEM_RULE = fixed | sim | auto overrides the choice below (tuning knob)
         const char* rule = getenv("EU_ITEM_RULE");
-        const bool rule_fixed = rule && std::strcmp(rule, "fixed") == 0;
-        const bool rule_sim = rule ? std::strcmp(rule, "sim") == 0 : h->cfg.world_size > 1;
+        // decomposed runs keep the fixed rule (the one measured at 2 and 8 GPUs) unless EU_ITEM_RULE=sim asks otherwise
+        const bool decomposed = h->cfg.world_size > 1;
+        const bool rule_fixed = (rule && std::strcmp(rule, "fixed") == 0) || (!rule && decomposed);
+        const bool sim_short = rule && std::strcmp(rule, "simshort") == 0;      // short pieces (6..16) + 4 % guard
+        const bool rule_sim = (rule && std::strcmp(rule, "sim") == 0) || sim_short;
         const char* e = getenv("EU_MARCH_LEN");
         if (e && atoi(e) > 0) {
             lmax = std::min(atoi(e), 4096);
@@ -532,7 +539,7 @@ int build_items(eu_handle h, int lo, int hi)
             const char* eh = getenv("EU_ITEM_HEAD");
             // start of a march in steps: two pieces of 15 beat four of 8 by 5 % at equal balance on a 32-plane slab -> ~0.75
             const double head = eh ? atof(eh) : 0.75;
-            const int L_lo = rule ? 4 : 6, L_hi = rule ? 48 : 16;
+            const int L_lo = sim_short ? 6 : 4, L_hi = sim_short ? 16 : 48;
             double best = 1e300;
             // the warps the persistent grid really has (3 blocks of 8 per SM, 2 with the capillary term)
             const int n_warps = h->n_sms*eu_fast_warps_per_sm(h->par.method_capillary != 0);
@@ -570,7 +577,7 @@ int build_items(eu_handle h, int lo, int hi)
                 const double mx = simulate(L);
                 if (mx < best) { best = mx; lmax = L; }
             }
-            if (!rule) {
+            if (sim_short) {
                 // Decomposed runs leave the fixed rule (the one measured at 2 and 8 GPUs) only where the model promises
                 // at least 4 %: a shorter piece also means more march heads, whose real cost the model only estimates.
                 int lfixed = 32;
@@ -655,6 +662,16 @@ int build_items(eu_handle h, int lo, int hi)
     }
     h->n_items = int(items.size());
     h->n_classes = int(classes.size());
+    h->plan_max_len = 0;
+    {
+        long long n_class_items = 0;
+        for (const int2& it : items) {
+            if (int(unsigned(it.y) >> 16) == EU_ITEM_GENERIC) continue;
+            h->plan_max_len = std::max(h->plan_max_len, it.y & 0xffff);
+            ++n_class_items;
+        }
+        h->plan_mean_len = n_class_items ? double(n_class_slices)/double(n_class_items) : 0.0;
+    }
     h->class_fraction = hi > lo ? double(n_class_slices)/double(hi - lo) : 0.0;
     if (items.empty()) items.push_back(make_int2(0, 0));
     if (classes.empty()) { EuSliceClass c; std::memset(&c, 0, sizeof(c)); classes.push_back(c); }
@@ -663,6 +680,7 @@ int build_items(eu_handle h, int lo, int hi)
     if ((rc = upload_vec(h, h->d_classes, classes))) return rc;
     h->items_lo = lo;
     h->items_hi = hi;
+    h->items_variant = variant_key;
     return EU_OK;
 }
 
@@ -973,6 +991,9 @@ int eu_grid_append(eu_handle h, const eu_grid_chunk* c)
 int eu_set_fluid(eu_handle h, const eu_fluid* f)
 {
     if (!h || !f) return EU_ERR_ARG;
+    // the mode-dependent structures (strict list / records, pc scale, axis check) are built in eu_grid_end from the
+    // fluid set before it: changing the fluid of a finished grid needs eu_grid_begin again (initObj re-flattens)
+    if (h->grid_ready) return fail(h, EU_ERR_ARG, "eu_set_fluid after eu_grid_end: upload the grid again (eu_grid_begin)");
     EU_CUDA(h, cudaSetDevice(h->cfg.device));
     if (f->mobility_kind != EU_MOB_SCALAR && f->mobility_kind != EU_MOB_DIAGONAL) return fail(h, EU_ERR_ARG, "bad mobility kind");
     if (f->n_rocks < 0 || f->n_rocks > EU_MAX_ROCKS) return fail(h, EU_ERR_UNSUPPORTED, "at most 16 rock types");
@@ -1073,8 +1094,8 @@ int eu_set_fluid(eu_handle h, const eu_fluid* f)
     h->fluid_set = true;
     h->contracted = false;
     h->cfl_cap_valid = h->cfl_grav_valid = false;
-    // arithmetic mode.  Tensor mobility: FAST needs axis-aligned face normals, decided in eu_grid_end once the grid is
-    // there (AUTO falls back to STRICT, an explicit FAST request fails); without rock tables the tensor class is
+    // arithmetic mode.  Tensor mobility: eu_grid_end picks the FAST variant once the grid is there (axis-aligned
+    // normals: scalar formula per face axis; oblique normals: k_fast_step_t3); without rock tables the tensor class is
     // isotropic (RockAnisotropicRelperm / ..._impl.hpp:86-101: the same quadratic curve in every direction) and runs
     // the scalar FAST path.
     h->tensor_fast = 0;
@@ -1257,6 +1278,16 @@ int eu_local_cells(eu_handle h) { return h ? h->n_local : 0; }
 int eu_resolved_mode(eu_handle h) { return (h && h->grid_ready) ? h->mode : EU_MODE_AUTO; }
 double eu_regular_fraction(eu_handle h) { return h ? h->regular_fraction : 0.0; }
 long long eu_local_halffaces(eu_handle h) { return h ? h->H : 0; }
+int eu_work_plan(eu_handle h, double out[4])
+{
+    if (!h || !out) return EU_ERR_ARG;
+    const bool have = h->mode == EU_MODE_FAST && h->items_lo >= 0;
+    out[0] = have ? h->class_fraction : 0.0;
+    out[1] = have ? double(h->n_items) : 0.0;
+    out[2] = have ? double(h->plan_max_len) : 0.0;
+    out[3] = have ? h->plan_mean_len : 0.0;
+    return EU_OK;
+}
 
 int eu_upload_saturation(eu_handle h, const double* saturation)
 {
@@ -1274,6 +1305,10 @@ int eu_upload_state(eu_handle h, const double* saturation, const double* hf_flux
     if (!h || !hf_flux) return EU_ERR_ARG;
     if (!h->grid_ready) return fail(h, EU_ERR_ARG, "grid not ready");
     EU_CUDA(h, cudaSetDevice(h->cfg.device));
+    if (!saturation && h->cur != 0) {
+        // the resident state stays (NULL saturation): after an odd number of substeps it lives in buffer 1
+        EU_CUDA(h, cudaMemcpyAsync(h->d_S[0].p, h->d_S[h->cur].p, size_t(h->n_local)*sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+    }
     h->cur = 0;                                  // every rank keeps the same buffer parity
     pin_host(h, hf_flux, size_t(h->H)*sizeof(double));
     if (saturation) pin_host(h, saturation, size_t(h->n_local)*sizeof(double));

@@ -114,6 +114,7 @@ def load_library():
     L.eu_local_halffaces.restype = C.c_longlong
     L.eu_regular_fraction.argtypes = [C.c_void_p]
     L.eu_regular_fraction.restype = C.c_double
+    L.eu_work_plan.argtypes = [C.c_void_p, _dp]
     L.eu_transport_solve.argtypes = [C.c_void_p, _dp, C.c_double, _dp, _dp, C.c_int, _ip, _dp, C.POINTER(_Report)]
     L.eu_upload_state.argtypes = [C.c_void_p, _dp, _dp]
     L.eu_upload_saturation.argtypes = [C.c_void_p, _dp]
@@ -393,6 +394,12 @@ class EulerUpstream:
 
     def regular_fraction(self):
         return float(self.L.eu_regular_fraction(self.h))
+
+    def work_plan(self):
+        """Work plan of the FAST substep kernel after the last substep: class fraction, items, longest / mean march."""
+        out = np.zeros(4)
+        self._check(self.L.eu_work_plan(self.h, _d(out)))
+        return {"class_fraction": float(out[0]), "items": int(out[1]), "max_march": int(out[2]), "mean_march": float(out[3])}
 
     def cfl_times(self, gravity):
         g = np.ascontiguousarray(gravity, dtype=np.float64)

@@ -33,6 +33,12 @@ def small_cases():
     cases.append(("c3_faulted_3rocks", c))
     c = synth.config_c4(12, 10, 8)              # config 3 at reduced size: heterogeneous perm, V+G
     cases.append(("c4_hetero_vg", c))
+    # march-active shapes (nx*ny a multiple of 32): the FAST kernel runs its z-march with the carried face flux, the
+    # code path bench.py times (k_fast_step<ROCKS, !MULTIROCK, !CAP> for V+G, <.., CAP> with the capillary term)
+    c = synth.config_c4(64, 16, 6)
+    cases.append(("c4_march_vg", c))
+    c = synth.config_c4(32, 32, 6, capillary=True)
+    cases.append(("c4_march_vgc", c))
     c = synth.random_geometry_case(6, 5, 4, seed=1, n_rocks=2, periodic=(True, False, True))
     cases.append(("rand_periodic_2rocks", c))
     c = synth.random_geometry_case(5, 5, 5, seed=3, n_rocks=0, periodic=(True, True, True))

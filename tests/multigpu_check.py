@@ -32,7 +32,11 @@ def main():
     cases = [("c2_cap", synth.config_c2(12)),
              ("zperiodic_2rocks", synth.random_geometry_case(6, 5, 2*world + 4, seed=41, n_rocks=2, periodic=(True, False, True))),
              ("faulted_3rocks", synth.config_c3(16, 12, 4*world)),
-             ("retry", synth.random_geometry_case(5, 4, 2*world + 2, seed=21, n_rocks=1, sources=False))]
+             ("retry", synth.random_geometry_case(5, 4, 2*world + 2, seed=21, n_rocks=1, sources=False)),
+             # march-active plane shapes (nx*ny % 32 == 0): slab interiors run the z-march the bench times, the planes next
+             # to a slab boundary the fused halo push
+             ("c4_march_vg", synth.config_c4(64, 16, 6*world)),
+             ("c4_march_vgc", synth.config_c4(32, 32, 6*world, capillary=True))]
     cases[3][1].max_steps = 2
     bad = 0
     for name, case in cases:

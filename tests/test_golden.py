@@ -49,8 +49,6 @@ def test_oracle_reproduces_golden(name, case):
 def test_cuda_reproduces_golden(name, case, mode):
     from opm_porsol_b200 import EulerUpstream
     from opm_porsol_b200.binding import params_from_case
-    if case.mobility_kind == 1 and mode == "fast":
-        pytest.skip("tensor mobility runs the STRICT kernels")
     g = golden(name)
     dev = EulerUpstream(device=0, mode=mode)
     dev.init(params_from_case(case))
