@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--cpu-substeps", type=int, default=16)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE configs in the line (C2, C3, C4+capillary)")
     return ap.parse_args()
 
 

@@ -181,8 +181,10 @@ int eu_resolved_mode(eu_handle h);
 double eu_regular_fraction(eu_handle h);
 /* the work plan of the FAST substep kernel, as built by the last substep / transportSolve (zeros before that and in
  * STRICT mode): out[0] = fraction of the own slices (32 cells) that belong to a slice class, out[1] = number of work
- * items, out[2] = longest march (slices per item), out[3] = mean march length over the class items.  Tests use it
- * to assert which code path a parity case exercised. */
+ * items, out[2] = longest march (slices per item), out[3] = mean march length over the class items.  When the box
+ * kernel ran (local numbering c = x + nx*(y + ny*z): tiles swept along z with TMA-staged operands) out[0] = 1, out[1] =
+ * work units (tile x z-chunk), out[2], out[3] = planes per unit.  Tests use it to assert which code path a parity case
+ * exercised; EU_BOX=0 in the environment keeps the slice-class kernel. */
 int eu_work_plan(eu_handle h, double out[4]);
 
 /* ---- EulerUpstream::transportSolve (EulerUpstream_impl.hpp:151-218) -------------------

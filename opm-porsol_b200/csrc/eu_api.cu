@@ -109,6 +109,13 @@ struct eu_solver {
     DevBuf<double2> d_qg;              // per unique face {flux of the current transportSolve, G}
     DevBuf<unsigned char> d_rock8;
     long long F = 0;
+    int axis[3] = { 0, 0, 0 };         // neighbour offsets of the axis planes of the face arrays (0 = none)
+    int max_slots = 0;                 // widest slice (canonical slots)
+    bool box_ok = false;               // local numbering is a box of whole planes (see eu_grid_end)
+    EuBoxPlan* box = nullptr;          // box kernel (eu_tile.cuh): tiles, tensor maps, work units; nullptr = slice-class kernel
+    bool ran_box = false;              // the last FAST substep ran the box kernel
+    int box_enabled = 1;               // EU_BOX=0 keeps the slice-class kernel (tuning / A-B knob)
+    DevBuf<unsigned short> d_cmask;    // per cell: record slots holding faces outside the axis planes
     int n_slices = 0;
     bool use_nn = false;
     int prefetch = 1;                  // EU_PREFETCH=<march steps ahead>, 0 turns the L2 prefetch of the marches off (tuning knob)
@@ -693,7 +700,16 @@ int launch_substep(eu_handle h, const EuStepArgs& a, bool exchange)
         eu_launch_fast_step_t3(g, h->tabf, h->fast(), a, h->own_lo/EU_SLICE, (h->own_hi + EU_SLICE - 1)/EU_SLICE, h->n_sms, h->st);
         return 1;
     }
+    if (h->mode == EU_MODE_FAST && h->box && !h->use_nn) {
+        // box numbering: plane sweep over tiles with TMA-staged operands (eu_tile.cuh)
+        EuHaloDev halo;
+        std::memset(&halo, 0, sizeof(halo));
+        const int nl = eu_launch_box_step(h->box, g, h->tabf, h->fast(), a, halo, h->cur, h->own_lo/EU_SLICE, 0, 0, h->st);
+        h->ran_box = nl >= 0;
+        return nl < 0 ? -1 : nl;
+    }
     if (h->mode == EU_MODE_FAST) {
+        h->ran_box = false;
         const int slice_lo = h->own_lo/EU_SLICE;
         const int slice_hi = (h->own_hi + EU_SLICE - 1)/EU_SLICE;
         EuHaloDev halo;
@@ -860,6 +876,7 @@ int eu_create(const eu_config* cfg, eu_handle* out)
     { const char* e = getenv("EU_PREFETCH"); if (e) h->prefetch = std::min(std::max(atoi(e), 0), 8); }
     { const char* e = getenv("EU_L2_HINT"); if (e) h->l2_hint = atoi(e) != 0; }
     { const char* e = getenv("EU_PIN_CACHE"); if (e) h->pin_cache = atoi(e) != 0; }
+    { const char* e = getenv("EU_BOX"); if (e) h->box_enabled = atoi(e) != 0; }
     std::memset(&h->fluid, 0, sizeof(h->fluid));
     std::memset(&h->tab, 0, sizeof(h->tab));
     if ((e = cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking)) != cudaSuccess ||
@@ -877,6 +894,8 @@ void eu_destroy(eu_handle h)
     cudaSetDevice(h->cfg.device);
     cudaStreamSynchronize(h->st);
     unpin_all(h);
+    eu_box_plan_destroy(h->box);
+    h->box = nullptr;
     for (eu_solver::Peer* p : h->peers) {
         for (void* o : p->opened) if (o) cudaIpcCloseMemHandle(o);
         delete p;
@@ -901,6 +920,8 @@ int eu_grid_begin(eu_handle h, int n_cells_global, int n_local_cells, long long 
         return fail(h, EU_ERR_ARG, "bad grid sizes (half-faces per rank must fit 32-bit)");
     EU_CUDA(h, cudaSetDevice(h->cfg.device));
     h->grid_open = true; h->grid_ready = false; h->state_ready = false; h->contracted = false;
+    eu_box_plan_destroy(h->box);
+    h->box = nullptr;
     h->cfl_cap_valid = h->cfl_grav_valid = false;
     h->n_global = n_cells_global; h->n_local_expected = n_local_cells; h->H_expected = n_local_halffaces;
     h->n_local = 0; h->H = 0;
@@ -1213,14 +1234,58 @@ int eu_grid_end(eu_handle h)
             if (rec_total > INT_MAX) return fail(h, EU_ERR_UNSUPPORTED, "too many half-face records for one GPU (32-bit)");
         }
         base[size_t(h->n_slices)] = int(rec_total);
-        // unique-face arrays: one plane per local face slot, indexed plane*n_local + owner cell
+        // unique-face arrays: three axis planes + one plane per local face slot, indexed plane*n_local + owner cell
+        planes += 3;
+        h->max_slots = planes - 3;
         h->F = (long long)planes*h->n_local;
         if (h->F > INT_MAX) return fail(h, EU_ERR_UNSUPPORTED, "face planes exceed 32-bit indexing on one GPU");
         if ((rc = upload_vec(h, h->d_slice_base, base))) return rc;
         EU_CUDA(h, h->d_rec.alloc(size_t(rec_total)));
         EU_CUDA(h, h->d_desc.alloc(size_t(rec_total/EU_SLICE) + 1));
         EU_CUDA(h, cudaMemsetAsync(h->d_flags.p, 0, 4*sizeof(int), h->st));
-        eu_launch_assign_fid(g, h->d_owner_hf.p, d_slot.p, h->d_fid_of_hf.p, h->st);
+        // axis planes: the three most common positive neighbour offsets (candidates: the offsets of the first, the
+        // middle and the last-but-one-plane own cell), each shared by at least a quarter of the cells
+        {
+            std::vector<int> cand;
+            const int samples[3] = { h->own_lo, h->own_lo + (h->own_hi - h->own_lo)/2, h->own_lo + (h->own_hi - h->own_lo)/3 };
+            for (int sc : samples) {
+                const int b = h->h_hf_offset[size_t(sc)], e = h->h_hf_offset[size_t(sc) + 1];
+                std::vector<int> nb(size_t(std::max(e - b, 1)));
+                if (e > b) EU_CUDA(h, cudaMemcpy(nb.data(), h->d_hf_nbr.p + b, size_t(e - b)*sizeof(int), cudaMemcpyDeviceToHost));
+                for (int k = 0; k < e - b; ++k) {
+                    const int d = nb[size_t(k)] - sc;
+                    if (nb[size_t(k)] > sc && cand.size() < 16 && std::find(cand.begin(), cand.end(), d) == cand.end()) cand.push_back(d);
+                }
+            }
+            h->axis[0] = h->axis[1] = h->axis[2] = 0;
+            if (!cand.empty()) {
+                DevBuf<int> d_cand;
+                DevBuf<unsigned long long> d_votes;
+                if ((rc = upload_vec(h, d_cand, cand))) return rc;
+                EU_CUDA(h, d_votes.alloc(16));
+                EU_CUDA(h, cudaMemsetAsync(d_votes.p, 0, 16*sizeof(unsigned long long), h->st));
+                eu_launch_offset_votes(g, d_cand.p, int(cand.size()), d_votes.p, h->st);
+                unsigned long long votes[16];
+                EU_CUDA(h, cudaMemcpyAsync(votes, d_votes.p, sizeof(votes), cudaMemcpyDeviceToHost, h->st));
+                EU_CUDA(h, cudaStreamSynchronize(h->st));
+                std::vector<int> order(cand.size());
+                for (size_t i = 0; i < order.size(); ++i) order[i] = int(i);
+                std::sort(order.begin(), order.end(), [&](int a, int b) { return votes[a] > votes[b]; });
+                std::vector<int> top;
+                for (size_t i = 0; i < order.size() && top.size() < 3; ++i)
+                    if (votes[order[i]]*4ULL >= (unsigned long long)h->n_local) top.push_back(cand[size_t(order[i])]);
+                std::sort(top.begin(), top.end());
+                // box numbering c = x + ax1*(y + ...): each axis offset must be a multiple of the one below
+                bool nested = true;
+                for (size_t i = 1; i < top.size(); ++i) nested = nested && top[i] % top[i - 1] == 0;
+                if (!top.empty() && top[0] == 1 && nested)
+                    for (size_t i = 0; i < top.size(); ++i) h->axis[i] = top[i];
+            }
+        }
+        // box numbering: local cell c = x + nx*(y + ny*z) over whole planes, own cells = whole planes (z-slab ranks with
+        // ghost planes, or a single rank); what the box kernel (eu_tile.cuh) needs
+        h->box_ok = h->axis[2] > 0 && h->n_local % h->axis[2] == 0 && h->own_lo % h->axis[2] == 0 && h->own_hi % h->axis[2] == 0;
+        eu_launch_assign_fid(g, h->d_owner_hf.p, d_slot.p, h->axis, h->box_ok ? 1 : 0, h->d_fid_of_hf.p, h->st);
         eu_launch_build_records(g, h->d_owner_hf.p, h->d_fid_of_hf.p, d_slot.p, h->d_slice_base.p, h->d_rec.p, h->d_desc.p,
                                 h->d_flags.p + 1, h->st);
         int nreg[4] = { 0, 0, 0, 0 };
@@ -1266,6 +1331,14 @@ int eu_grid_end(eu_handle h)
     EU_CUDA(h, h->d_residual.alloc(n));
     EU_CUDA(h, h->d_block_min.alloc(size_t(eu_cfl_blocks(h->n_local))));
     EU_CUDA(h, h->d_fail_key.alloc(1));
+    if (h->mode == EU_MODE_FAST && !h->tensor_fast && h->box_ok && h->box_enabled && h->max_slots <= 16 && h->cfg.world_size <= 1) {
+        // box kernel: per-cell mask of the faces outside the axis planes, tensor maps over the state and face arrays
+        EU_CUDA(h, h->d_cmask.alloc(n));
+        eu_launch_cell_mask(h->grid(), h->d_slice_base.p, h->d_rec.p, h->d_cmask.p, h->st);
+        const int nx = h->axis[1], ny = h->axis[2]/h->axis[1], nz = h->n_local/h->axis[2];
+        h->box = eu_box_plan_create(nx, ny, nz, h->own_lo/h->axis[2], h->own_hi/h->axis[2], h->d_S[0].p, h->d_S[1].p, h->d_pc[0].p,
+                                    h->d_pc[1].p, h->d_qg.p, h->d_T.p, h->d_cmask.p, h->n_sms);
+    }
     EU_CUDA(h, cudaStreamSynchronize(h->st));
     EU_CUDA(h, cudaGetLastError());
     h->grid_open = false;
@@ -1281,6 +1354,18 @@ long long eu_local_halffaces(eu_handle h) { return h ? h->H : 0; }
 int eu_work_plan(eu_handle h, double out[4])
 {
     if (!h || !out) return EU_ERR_ARG;
+    if (h->mode == EU_MODE_FAST && h->ran_box && h->box) {
+        // box kernel: every own cell is swept by a tile; items = work units, march = planes per unit
+        int info[6];
+        eu_box_plan_info(h->box, info);
+        out[0] = 1.0;
+        out[1] = double(info[2]);
+        const int planes = (h->own_hi - h->own_lo)/h->axis[2];
+        const int tiles = ((h->axis[1] + info[0] - 1)/info[0])*((h->axis[2]/h->axis[1] + info[1] - 1)/info[1]);
+        out[3] = info[2] > 0 ? double(planes)*tiles/double(info[2]) : 0.0;
+        out[2] = std::ceil(out[3]);
+        return EU_OK;
+    }
     const bool have = h->mode == EU_MODE_FAST && h->items_lo >= 0;
     out[0] = have ? h->class_fraction : 0.0;
     out[1] = have ? double(h->n_items) : 0.0;

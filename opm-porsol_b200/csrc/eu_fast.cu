@@ -15,7 +15,11 @@
 // before any arithmetic, so a warp has 6-8 independent loads per lane in flight instead of a chain.
 #include "eu_internal.h"
 
+#include <algorithm>
+#include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <vector>
 
 namespace {
 
@@ -918,6 +922,251 @@ __global__ void __launch_bounds__(kBlock) k_fast_state(EuGridDev g, EuTablesDev 
 }
 
 } // namespace
+
+#include "eu_tile.cuh"
+
+// ---- box kernel: host side -------------------------------------------------------------------------------------
+struct EuBoxPlan {
+    int nx = 0, ny = 0, nz = 0, z_lo = 0, z_hi = 0, n_local = 0;
+    int tx = 0, ty = 0, threads = 0;
+    CUtensorMap mapS[2], mapPc[2], mapQG, mapT;
+    int4* d_units = nullptr;
+    int n_units = 0, n_bnd_units[2] = { 0, 0 };
+    int units_key[5] = { -1, -1, -1, -1, -1 };      // (bnd planes lo, hi, grid blocks, lz override, cap) the unit list was built for
+    const unsigned short* cmask = nullptr;
+    int n_sms = 148;
+};
+
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        cudaGetLastError();
+    }
+    return fn;
+}
+
+// tensor map over doubles: dims / box innermost first, strides in bytes for dims 1..rank-1
+bool make_map(CUtensorMap* m, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box)
+{
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    cuuint32_t ones[5] = { 1, 1, 1, 1, 1 };
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, cuuint32_t(rank), base, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+inline int r128(int v) { return (v + 127) & ~127; }
+
+// shared-memory layout of the box kernel for a tile shape
+struct BoxLayout { EuBoxDev b; size_t total; };
+BoxLayout box_layout(const EuBoxPlan& p, bool cap, bool multirock, int stages, size_t tab_bytes)
+{
+    BoxLayout o;
+    std::memset(&o, 0, sizeof(o));
+    EuBoxDev& b = o.b;
+    b.nx = p.nx; b.ny = p.ny; b.nz = p.nz; b.tx = p.tx; b.ty = p.ty;
+    b.stages = stages;
+    const int cells = (p.tx + 2)*(p.ty + 2);
+    b.lam_bytes = r128(cells*(cap ? 32 : 16));
+    b.rk_bytes = (cap && multirock) ? r128(cells) : 0;
+    b.qg_bytes = r128((p.tx + 1)*(p.ty + 1)*16);
+    b.T_bytes = cap ? r128((p.tx + 2)*(p.ty + 1)*8) : 0;
+    const int S_bytes = r128((p.tx + 4)*(p.ty + 2)*8);
+    b.off_S = 0;
+    b.off_pc = S_bytes;
+    b.off_qg = S_bytes*(cap ? 2 : 1);
+    b.off_T = b.off_qg + 3*b.qg_bytes;
+    b.stage_bytes = b.off_T + 3*b.T_bytes;
+    b.off_bar = 0;
+    b.off_lam = 128;
+    b.off_rk = b.off_lam + 3*b.lam_bytes;
+    b.off_stage = b.off_rk + 3*b.rk_bytes;
+    o.total = tab_bytes + 128 /* alignment slack */ + size_t(b.off_stage) + size_t(stages)*size_t(b.stage_bytes);
+    return o;
+}
+
+} // namespace
+
+void eu_box_plan_destroy(EuBoxPlan* p)
+{
+    if (!p) return;
+    if (p->d_units) cudaFree(p->d_units);
+    delete p;
+}
+
+// nullptr when the box kernel does not apply (then the slice-class kernel runs)
+EuBoxPlan* eu_box_plan_create(int nx, int ny, int nz, int z_lo, int z_hi, double* S0, double* S1, double* pc0, double* pc1,
+                              double2* qg, double* T, const unsigned short* cmask, int n_sms)
+{
+    // TMA: global strides are multiples of 16 bytes (nx even); coordinates fit the unit encoding
+    if (nx < 2 || (nx & 1) || ny < 1 || nz < 1 || nx > 65535 || ny > 32767) return nullptr;
+    if (!encode_tiled_fn()) return nullptr;
+    EuBoxPlan* p = new EuBoxPlan;
+    p->nx = nx; p->ny = ny; p->nz = nz; p->z_lo = z_lo; p->z_hi = z_hi; p->n_local = nx*ny*nz;
+    p->cmask = cmask; p->n_sms = n_sms;
+    // tile: tx even, 2(tx+1) <= 256 (TMA box limit), tx*ty <= 256 threads; minimise (halo overhead) x (idle threads)
+    {
+        const char* e = getenv("EU_BOX_TILE");          // "tx,ty" (tuning knob)
+        int etx = 0, ety = 0;
+        if (e && std::sscanf(e, "%d,%d", &etx, &ety) == 2 && etx >= 2 && !(etx & 1) && etx <= 126 && ety >= 1 && etx*ety <= 256) {
+            p->tx = etx; p->ty = ety;
+        } else {
+            double best = 1e300;
+            for (int tx = 2; tx <= 126 && tx <= ((nx + 1) & ~1); tx += 2) {
+                for (int ty = 1; ty <= 32 && tx*ty <= 256 && ty <= ny; ++ty) {
+                    const double halo = double((tx + 2)*(ty + 2))/double(tx*ty);
+                    const double idle_x = double(((nx + tx - 1)/tx)*tx)/nx, idle_y = double(((ny + ty - 1)/ty)*ty)/ny;
+                    const double warps = double((tx*ty + 31)/32*32)/double(tx*ty);
+                    // curve evaluations are about a fifth of a cell's work; idle lanes cost everything; a tile row that
+                    // is a multiple of 32 cells keeps the warps' shared-memory rows conflict-free
+                    double cost = (0.8 + 0.2*halo)*idle_x*idle_y*warps*(tx*ty < 128 ? 1.3 : 1.0)*((tx % 32) ? 1.03 : 1.0);
+                    if (cost < best - 1e-12) { best = cost; p->tx = tx; p->ty = ty; }
+                }
+            }
+        }
+        p->threads = (p->tx*p->ty + 31)/32*32;
+    }
+    const cuuint64_t n = cuuint64_t(p->n_local);
+    bool ok = true;
+    {
+        cuuint64_t dims[3] = { cuuint64_t(nx), cuuint64_t(ny), cuuint64_t(nz) };
+        cuuint64_t str[2] = { cuuint64_t(nx)*8, cuuint64_t(nx)*ny*8 };
+        cuuint32_t box[3] = { cuuint32_t(p->tx + 4), cuuint32_t(p->ty + 2), 1 };      // starts at x0 - 2: even coordinate
+        ok = ok && make_map(&p->mapS[0], S0, 3, dims, str, box) && make_map(&p->mapS[1], S1, 3, dims, str, box);
+        ok = ok && make_map(&p->mapPc[0], pc0, 3, dims, str, box) && make_map(&p->mapPc[1], pc1, 3, dims, str, box);
+    }
+    {
+        cuuint64_t dims[4] = { cuuint64_t(2*nx), cuuint64_t(ny), cuuint64_t(nz), 3 };
+        cuuint64_t str[3] = { cuuint64_t(nx)*16, cuuint64_t(nx)*ny*16, n*16 };
+        cuuint32_t box[4] = { cuuint32_t(2*(p->tx + 1)), cuuint32_t(p->ty + 1), 1, 1 };
+        ok = ok && make_map(&p->mapQG, qg, 4, dims, str, box);
+    }
+    {
+        cuuint64_t dims[4] = { cuuint64_t(nx), cuuint64_t(ny), cuuint64_t(nz), 3 };
+        cuuint64_t str[3] = { cuuint64_t(nx)*8, cuuint64_t(nx)*ny*8, n*8 };
+        cuuint32_t box[4] = { cuuint32_t(p->tx + 2), cuuint32_t(p->ty + 1), 1, 1 };
+        ok = ok && make_map(&p->mapT, T, 4, dims, str, box);
+    }
+    if (!ok) { eu_box_plan_destroy(p); return nullptr; }
+    return p;
+}
+
+void eu_box_plan_info(const EuBoxPlan* p, int out[6])
+{
+    out[0] = p->tx; out[1] = p->ty; out[2] = p->n_units; out[3] = p->n_bnd_units[0]; out[4] = p->n_bnd_units[1]; out[5] = p->threads;
+}
+
+// Work units: tiles x z-chunks.  The planes next to a slab boundary (bnd_lo / bnd_hi planes at the two ends of the own
+// range; 0 without a neighbour rank) form short chunks that come first in the list: their results are pushed to the
+// neighbour rank.  The chunk length of the rest balances (units per block) x (planes + 1 prologue step per unit).
+static int box_build_units(EuBoxPlan* p, int bnd_lo, int bnd_hi, int grid_blocks, bool cap)
+{
+    const char* e = getenv("EU_BOX_LZ");
+    const int lz_env = e ? atoi(e) : 0;
+    if (p->units_key[0] == bnd_lo && p->units_key[1] == bnd_hi && p->units_key[2] == grid_blocks && p->units_key[3] == lz_env &&
+        p->units_key[4] == int(cap) && p->d_units) return 0;
+    const int tiles_x = (p->nx + p->tx - 1)/p->tx, tiles_y = (p->ny + p->ty - 1)/p->ty;
+    const int tiles = tiles_x*tiles_y;
+    const int zi0 = p->z_lo + bnd_lo, zi1 = p->z_hi - bnd_hi;          // interior planes
+    int lz = 32;
+    if (lz_env > 0) lz = lz_env;
+    else if (zi1 > zi0) {
+        double best = 1e300;
+        for (int L = 4; L <= 64; ++L) {
+            const long long chunks = (zi1 - zi0 + L - 1)/L;
+            const long long units = chunks*tiles;
+            const double rounds = double((units + grid_blocks - 1)/grid_blocks);
+            const double len = double(zi1 - zi0)/double(chunks);
+            const double cost = rounds*(len + 1.3);
+            if (cost < best - 1e-9) { best = cost; lz = L; }
+        }
+    }
+    std::vector<int4> units;
+    auto add = [&](int z0, int z1, int flags) {
+        for (int tyi = 0; tyi < tiles_y; ++tyi)
+            for (int txi = 0; txi < tiles_x; ++txi)
+                units.push_back(make_int4((txi*p->tx) | ((tyi*p->ty) << 16), z0, z1, flags));
+    };
+    p->n_bnd_units[0] = p->n_bnd_units[1] = 0;
+    if (bnd_lo > 0) { add(p->z_lo, std::min(p->z_lo + bnd_lo, p->z_hi), 1); p->n_bnd_units[0] = tiles; }
+    if (bnd_hi > 0 && zi1 >= zi0) { add(std::max(zi1, p->z_lo + bnd_lo), p->z_hi, 2); p->n_bnd_units[1] = tiles; }
+    if (zi1 > zi0) {
+        const int chunks = (zi1 - zi0 + lz - 1)/lz;
+        for (int q = 0; q < chunks; ++q) {
+            const int a0 = zi0 + int((long long)(zi1 - zi0)*q/chunks), a1 = zi0 + int((long long)(zi1 - zi0)*(q + 1)/chunks);
+            if (a1 > a0) add(a0, a1, 0);
+        }
+    }
+    if (p->d_units) { cudaFree(p->d_units); p->d_units = nullptr; }
+    p->n_units = int(units.size());
+    if (units.empty()) return 0;
+    if (cudaMalloc((void**)&p->d_units, units.size()*sizeof(int4)) != cudaSuccess) return -1;
+    if (cudaMemcpy(p->d_units, units.data(), units.size()*sizeof(int4), cudaMemcpyHostToDevice) != cudaSuccess) return -1;
+    p->units_key[0] = bnd_lo; p->units_key[1] = bnd_hi; p->units_key[2] = grid_blocks; p->units_key[3] = lz_env; p->units_key[4] = int(cap);
+    return 0;
+}
+
+template <bool ROCKS, bool MULTIROCK, bool CAP>
+static int launch_box(EuBoxPlan* p, const EuGridDev& g, const EuTablesDev& t, const EuFastDev& f, const EuStepArgs& a,
+                      const EuHaloDev& halo, int cur, int slice_lo, int bnd_lo, int bnd_hi, cudaStream_t st)
+{
+    auto kern = k_box_step<ROCKS, MULTIROCK, CAP>;
+    const size_t tab_bytes = eu_fast_smem_bytes(t);
+    static int stages_env = -1;
+    if (stages_env < 0) { const char* e = getenv("EU_BOX_STAGES"); stages_env = e ? std::min(std::max(atoi(e), 2), 6) : 0; }
+    // as many bundles in flight as still leave the kernel's resident blocks per SM (3, or 2 with the capillary term)
+    const int want_blocks = CAP ? 2 : 3;
+    int stages = stages_env ? stages_env : 3;
+    BoxLayout lay = box_layout(*p, CAP, MULTIROCK, stages, tab_bytes);
+    const size_t budget = size_t(227*1024)/want_blocks - 1024;
+    while (!stages_env && stages > 2 && lay.total > budget) lay = box_layout(*p, CAP, MULTIROCK, --stages, tab_bytes);
+    static size_t smem_set = 0;
+    if (lay.total > smem_set) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total) != cudaSuccess) return -1;
+        smem_set = lay.total;
+    }
+    int blocks_per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, p->threads, lay.total);
+    if (blocks_per_sm < 1) return -1;
+    const int grid_full = p->n_sms*blocks_per_sm;
+    if (box_build_units(p, bnd_lo, bnd_hi, grid_full, CAP)) return -1;
+    if (p->n_units == 0) return 0;
+    lay.b.units = p->d_units;
+    lay.b.n_units = p->n_units;
+    lay.b.cmask = p->cmask;
+    const int blocks = std::min(grid_full, p->n_units);
+    kern<<<blocks, p->threads, lay.total, st>>>(p->mapS[cur], p->mapPc[cur], p->mapQG, p->mapT, g, t, f, a, halo, lay.b, slice_lo, (int)tab_bytes);
+    return 1;
+}
+
+// one substep of the own planes [z_lo, z_hi) with the box kernel; returns the number of launches, -1 on error
+int eu_launch_box_step(EuBoxPlan* p, const EuGridDev& g, const EuTablesDev& t, const EuFastDev& f, const EuStepArgs& a,
+                       const EuHaloDev& halo, int cur, int slice_lo, int bnd_lo, int bnd_hi, cudaStream_t st)
+{
+    const bool cap = a.method_capillary != 0;
+    if (t.n_rocks > 1) {
+        return cap ? launch_box<true, true, true>(p, g, t, f, a, halo, cur, slice_lo, bnd_lo, bnd_hi, st)
+                   : launch_box<true, true, false>(p, g, t, f, a, halo, cur, slice_lo, bnd_lo, bnd_hi, st);
+    } else if (t.n_rocks == 1) {
+        return cap ? launch_box<true, false, true>(p, g, t, f, a, halo, cur, slice_lo, bnd_lo, bnd_hi, st)
+                   : launch_box<true, false, false>(p, g, t, f, a, halo, cur, slice_lo, bnd_lo, bnd_hi, st);
+    }
+    return cap ? launch_box<false, false, true>(p, g, t, f, a, halo, cur, slice_lo, bnd_lo, bnd_hi, st)
+               : launch_box<false, false, false>(p, g, t, f, a, halo, cur, slice_lo, bnd_lo, bnd_hi, st);
+}
 
 bool eu_fast_uses_stored_lam() { return kStoredLam; }
 

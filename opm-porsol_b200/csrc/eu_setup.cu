@@ -226,15 +226,76 @@ __global__ void k_canonical_slots(EuGridDev g, unsigned char* __restrict__ slot_
     if (lane == 0) slice_width[warp] = width;
 }
 
-// face id of an own half-face = slot*n_local + cell ("plane" = canonical slot of the owner's half-face): coalesced per
-// plane, and for a regular neighbour pattern the id of the neighbour's twin face is affine in the cell index
+// Axis planes of the face arrays.  The (up to) three most common positive neighbour offsets of the grid -- 1, nx and
+// nx*ny for a logically Cartesian numbering, whatever the grid interface calls its faces -- get the face planes 0, 1, 2:
+// the face between cell c and cell c + ax[a] lives at a*n_local + c wherever it exists, and entries of cells without
+// such a face stay zero (zero flux, G and T).  Every other face (boundary, fault, periodic wrap, split faces) lives in
+// plane 3 + its canonical slot.  With that the regular faces of the whole grid are three dense arrays indexed by the
+// lower cell, uniform across slices and planes: slice classes merge, and the box kernel (eu_tile.cuh) reads them as
+// tiles.  `box` = {nx, nx*ny} restricts the axis planes to offsets that stay inside a row / plane of the box numbering.
+__global__ void k_offset_votes(EuGridDev g, const int* __restrict__ cand, int n_cand, unsigned long long* __restrict__ votes)
+{
+    __shared__ unsigned int sv[16];
+    if (threadIdx.x < 16) sv[threadIdx.x] = 0u;
+    __syncthreads();
+    const int c = blockIdx.x*blockDim.x + threadIdx.x;
+    if (c < g.n_local) {
+        const int b = g.hf_offset[c], e = g.hf_offset[c + 1];
+        for (int h = b; h < e; ++h) {
+            const int n = g.hf_nbr[h];
+            if (n <= c) continue;
+            const int d = n - c;
+            for (int q = 0; q < n_cand; ++q) if (cand[q] == d) atomicAdd(&sv[q], 1u);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < n_cand && sv[threadIdx.x]) atomicAdd(votes + threadIdx.x, (unsigned long long)sv[threadIdx.x]);
+}
+
+// face id of an own half-face: axis plane (see above) or (3 + canonical slot)*n_local + cell
 __global__ void k_assign_fid(EuGridDev g, const int* __restrict__ owner_hf, const unsigned char* __restrict__ slot_of_hf,
-                             int* __restrict__ fid_of_hf)
+                             int ax0, int ax1, int ax2, int box, int* __restrict__ fid_of_hf)
 {
     int c = blockIdx.x*blockDim.x + threadIdx.x;
     if (c >= g.n_local) return;
     const int b = g.hf_offset[c], e = g.hf_offset[c + 1];
-    for (int h = b; h < e; ++h) fid_of_hf[h] = (owner_hf[h] == h) ? int(slot_of_hf[h])*g.n_local + c : -1;
+    unsigned taken = 0u;
+    for (int h = b; h < e; ++h) {
+        int fid = -1;
+        if (owner_hf[h] == h) {
+            fid = (3 + int(slot_of_hf[h]))*g.n_local + c;
+            const int n = g.hf_nbr[h];
+            if (n > c) {
+                const int d = n - c;
+                int a = -1;
+                // the offset must stay inside the row (a = 0) / plane (a = 1) of the box numbering c = x + ax1*(y + ..)
+                // (only when the local numbering is a box, `box`: otherwise c % ax1 says nothing about the row)
+                if (ax0 > 0 && d == ax0 && (!box || (c % ax1) + ax0 < ax1)) a = 0;
+                else if (ax1 > 0 && d == ax1 && (!box || (c % ax2) + ax1 < ax2)) a = 1;
+                else if (ax2 > 0 && d == ax2) a = 2;
+                if (a >= 0 && !((taken >> a) & 1u)) { taken |= 1u << a; fid = a*g.n_local + c; }
+            }
+        }
+        fid_of_hf[h] = fid;
+    }
+}
+
+// per cell: which record slots (SELL slot j < 16) hold a face that is NOT in an axis plane -- the faces the box kernel
+// adds one by one from the records after its regular faces
+__global__ void k_cell_mask(EuGridDev g, const int* __restrict__ slice_base, const int2* __restrict__ rec,
+                            unsigned short* __restrict__ cmask)
+{
+    const int c = blockIdx.x*blockDim.x + threadIdx.x;
+    if (c >= g.n_local) return;
+    const int s = c >> 5, lane = c & 31;
+    const int base = slice_base[s];
+    const int width = (slice_base[s + 1] - base) >> 5;
+    unsigned m = 0u;
+    for (int j = 0; j < width && j < 16; ++j) {
+        const int2 r = rec[(long long)base + (long long)j*EU_SLICE + lane];
+        if (r.x != EU_REC_PAD && r.y >= 3*g.n_local) m |= 1u << j;
+    }
+    cmask[c] = (unsigned short)m;
 }
 
 __global__ void k_build_records(EuGridDev g, const int* __restrict__ owner_hf, const int* __restrict__ fid_of_hf,
@@ -820,9 +881,18 @@ void eu_launch_canonical_slots(const EuGridDev& g, unsigned char* slot_of_hf, in
     const int n_slices = (g.n_local + EU_SLICE - 1)/EU_SLICE;
     k_canonical_slots<<<div_up((long long)n_slices*32, kThreads), kThreads, 0, st>>>(g, slot_of_hf, slice_width);
 }
-void eu_launch_assign_fid(const EuGridDev& g, const int* owner_hf, const unsigned char* slot_of_hf, int* fid_of_hf, cudaStream_t st)
+void eu_launch_assign_fid(const EuGridDev& g, const int* owner_hf, const unsigned char* slot_of_hf, const int ax[3], int box,
+                          int* fid_of_hf, cudaStream_t st)
 {
-    k_assign_fid<<<div_up(g.n_local, kThreads), kThreads, 0, st>>>(g, owner_hf, slot_of_hf, fid_of_hf);
+    k_assign_fid<<<div_up(g.n_local, kThreads), kThreads, 0, st>>>(g, owner_hf, slot_of_hf, ax[0], ax[1], ax[2], box, fid_of_hf);
+}
+void eu_launch_offset_votes(const EuGridDev& g, const int* cand, int n_cand, unsigned long long* votes, cudaStream_t st)
+{
+    k_offset_votes<<<div_up(g.n_local, kThreads), kThreads, 0, st>>>(g, cand, n_cand, votes);
+}
+void eu_launch_cell_mask(const EuGridDev& g, const int* slice_base, const int2* rec, unsigned short* cmask, cudaStream_t st)
+{
+    k_cell_mask<<<div_up(g.n_local, kThreads), kThreads, 0, st>>>(g, slice_base, rec, cmask);
 }
 void eu_launch_build_records(const EuGridDev& g, const int* owner_hf, const int* fid_of_hf, const unsigned char* slot_of_hf,
                              const int* slice_base, int2* rec, int2* desc, int* n_regular_slots, cudaStream_t st)

@@ -365,9 +365,10 @@ class EulerUpstream:
 
     # -- device-resident variant
     def upload_state(self, saturation, hf_flux):
-        s = np.ascontiguousarray(saturation, dtype=np.float64)
+        """saturation=None keeps the resident state and replaces the fluxes only (the IMPES loop between pressure solves)."""
+        s = None if saturation is None else np.ascontiguousarray(saturation, dtype=np.float64)
         fl = np.ascontiguousarray(hf_flux, dtype=np.float64)
-        self._check(self.L.eu_upload_state(self.h, _d(s), _d(fl)))
+        self._check(self.L.eu_upload_state(self.h, None if s is None else _d(s), _d(fl)))
 
     def upload_saturation(self, saturation):
         s = np.ascontiguousarray(saturation, dtype=np.float64)

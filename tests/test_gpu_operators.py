@@ -85,3 +85,37 @@ def test_diagnostics_bit_exact(name, case, mode):
     assert np.array_equal(dev.computeCapPressures(sat_b), port.cap_pressures(sat_b))
     assert np.array_equal(dev.download_saturation(), case.sat0)
     dev.close()
+
+
+@pytest.mark.parametrize("mode", ["strict", "fast"])
+def test_resident_state_survives_flux_only_upload_after_odd_substeps(mode):
+    """IMPES loop with the state resident: transportSolve (odd number of substeps, so the state ends in the second
+    ping-pong buffer), new fluxes with eu_upload_state(h, NULL, flux), transportSolve again.  Must equal two
+    consecutive transportSolves of the oracle."""
+    from opm_porsol_b200 import EulerUpstream, synth
+    from opm_porsol_b200.binding import params_from_case
+    from oracle.ref import PortSolver
+    case = synth.config_c4(32, 32, 6, capillary=True)
+    case.min_steps = case.max_steps = 3
+    port = PortSolver(case)
+    fac = port.compute_cfl_factors()
+    time = 1.2*min(port.cfl_times())*case.courant
+    flux2 = 0.5*case.hf_flux
+    a = port.transport_solve(case.sat0, time=time)
+    b = port.transport_solve(a["sat"], time=time, hf_flux=flux2)
+    assert a["nsteps"] == b["nsteps"] == 3
+    dev = EulerUpstream(device=0, mode=mode)
+    dev.init(params_from_case(case))
+    dev.initObj(case, cfl_factors=fac)
+    dev.upload_state(case.sat0, case.hf_flux)
+    r1 = dev.transportSolveResident(time, case.gravity)
+    dev.upload_state(None, flux2)
+    r2 = dev.transportSolveResident(time, case.gravity)
+    assert r1.nsteps == r2.nsteps == 3
+    sat = dev.download_saturation()
+    if mode == "strict":
+        assert np.array_equal(sat, b["sat"])
+    else:
+        assert np.abs(sat - b["sat"]).max() <= 1e-9
+    assert np.abs(sat - a["sat"]).max() > 1e-6        # the second solve did move the state
+    dev.close()
