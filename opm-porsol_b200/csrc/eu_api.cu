@@ -700,7 +700,7 @@ int launch_substep(eu_handle h, const EuStepArgs& a, bool exchange)
         eu_launch_fast_step_t3(g, h->tabf, h->fast(), a, h->own_lo/EU_SLICE, (h->own_hi + EU_SLICE - 1)/EU_SLICE, h->n_sms, h->st);
         return 1;
     }
-    if (h->mode == EU_MODE_FAST && h->box && !h->use_nn) {
+    if (h->mode == EU_MODE_FAST && h->box && !h->use_nn && a.method_viscous) {      // (the box kernel has the viscous term built in)
         // box numbering: plane sweep over tiles with TMA-staged operands (eu_tile.cuh)
         EuHaloDev halo;
         std::memset(&halo, 0, sizeof(halo));

@@ -54,7 +54,7 @@ extern __shared__ __align__(16) unsigned char eu_smem[];
 struct TabLayout {
     int nn;          // nodes over all rocks
     int nb;          // buckets per rock
-    int shift;       // unused
+    double nbd;      // nb as a double (hoisted conversion)
     __device__ __forceinline__ const double4* coef() const { return reinterpret_cast<const double4*>(eu_smem); }
     __device__ __forceinline__ const double2* jcoef() const { return reinterpret_cast<const double2*>(eu_smem + size_t(32)*nn); }
     __device__ __forceinline__ const double* xb() const { return reinterpret_cast<const double*>(eu_smem + size_t(48)*nn); }
@@ -82,7 +82,7 @@ __device__ __forceinline__ void tables_to_smem(const EuTablesDev& t)
 template <bool MULTIROCK>
 __device__ __forceinline__ int interval(const TabLayout& L, int rock, double sat)
 {
-    int k = __double2int_rd(sat*double(L.nb));
+    int k = __double2int_rd(sat*L.nbd);
     k = min(max(k, 0), L.nb - 1);
     const int b = MULTIROCK ? L.offset()[rock] : 0;
     int j = b + L.bucket()[(MULTIROCK ? rock*L.nb : 0) + k];
@@ -680,7 +680,7 @@ __global__ void __launch_bounds__(kBlock, MINB) k_fast_step(EuGridDev g, EuTable
                                                             EuHaloDev halo, int slice_lo, int slice_hi, int class_smem_offset)
 {
     TabLayout L;
-    L.nn = t.n_nodes_total; L.nb = t.n_buckets; L.shift = 0;
+    L.nn = t.n_nodes_total; L.nb = t.n_buckets; L.nbd = double(t.n_buckets);
     if (ROCKS) tables_to_smem(t);
     EuSliceClass* classes = reinterpret_cast<EuSliceClass*>(eu_smem + class_smem_offset);
     {
@@ -810,7 +810,7 @@ __global__ void __launch_bounds__(kBlock, 2) k_fast_step_t3(EuGridDev g, EuTable
                                                             int slice_lo, int slice_hi)
 {
     TabLayout L;
-    L.nn = t.n_nodes_total; L.nb = t.n_buckets; L.shift = 0;
+    L.nn = t.n_nodes_total; L.nb = t.n_buckets; L.nbd = double(t.n_buckets);
     tables_to_smem(t);
     __syncthreads();
     {
@@ -906,7 +906,7 @@ __global__ void __launch_bounds__(kBlock) k_fast_state(EuGridDev g, EuTablesDev 
                                                        double2* __restrict__ lam, int lo, int hi)
 {
     TabLayout L;
-    L.nn = t.n_nodes_total; L.nb = t.n_buckets; L.shift = 0;
+    L.nn = t.n_nodes_total; L.nb = t.n_buckets; L.nbd = double(t.n_buckets);
     if (ROCKS) {
         tables_to_smem(t);
         __syncthreads();
@@ -1123,20 +1123,20 @@ template <bool ROCKS, bool MULTIROCK, bool CAP>
 static int launch_box(EuBoxPlan* p, const EuGridDev& g, const EuTablesDev& t, const EuFastDev& f, const EuStepArgs& a,
                       const EuHaloDev& halo, int cur, int slice_lo, int bnd_lo, int bnd_hi, cudaStream_t st)
 {
-    auto kern = k_box_step<ROCKS, MULTIROCK, CAP>;
     const size_t tab_bytes = eu_fast_smem_bytes(t);
     static int stages_env = -1;
-    if (stages_env < 0) { const char* e = getenv("EU_BOX_STAGES"); stages_env = e ? std::min(std::max(atoi(e), 2), 6) : 0; }
-    // as many bundles in flight as still leave the kernel's resident blocks per SM (3, or 2 with the capillary term)
+    if (stages_env < 0) { const char* e = getenv("EU_BOX_STAGES"); stages_env = e ? std::min(std::max(atoi(e), 2), 4) : 0; }
+    // as many bundles in flight (2..4) as still leave the kernel's resident blocks per SM (3, or 2 with the capillary term)
     const int want_blocks = CAP ? 2 : 3;
     int stages = stages_env ? stages_env : 3;
     BoxLayout lay = box_layout(*p, CAP, MULTIROCK, stages, tab_bytes);
     const size_t budget = size_t(227*1024)/want_blocks - 1024;
     while (!stages_env && stages > 2 && lay.total > budget) lay = box_layout(*p, CAP, MULTIROCK, --stages, tab_bytes);
-    static size_t smem_set = 0;
-    if (lay.total > smem_set) {
+    auto kern = stages == 2 ? k_box_step<ROCKS, MULTIROCK, CAP, 2> : (stages == 3 ? k_box_step<ROCKS, MULTIROCK, CAP, 3> : k_box_step<ROCKS, MULTIROCK, CAP, 4>);
+    static size_t smem_set[5] = { 0, 0, 0, 0, 0 };
+    if (lay.total > smem_set[stages]) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total) != cudaSuccess) return -1;
-        smem_set = lay.total;
+        smem_set[stages] = lay.total;
     }
     int blocks_per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, p->threads, lay.total);

@@ -76,20 +76,76 @@ __device__ __forceinline__ void tma_load_4d(unsigned dst, const CUtensorMap* map
                  :: "r"(dst), "l"(map), "r"(x), "r"(y), "r"(z), "r"(w), "r"(bar) : "memory");
 }
 
+// G == 0 (no gravity component through the face: every lateral face of a grid with horizontal layers): both phases are
+// upwinded by the sign of q alone.  Bit-identical to face_regular for G == 0.
+template <bool OWN, bool CAP>
+__device__ __forceinline__ double face_no_gravity(double q, double lw0, double lo0, double lw1, double lo1, double cap_coef, double Tdpc)
+{
+    const bool from_self = (q >= 0.0) == OWN;
+    const double cw = from_self ? lw0 : lw1, co = from_self ? lo0 : lo1;
+    double dS = div_pos(cw*q, cw + co);
+    if (CAP) dS = fma(cap_coef, Tdpc, dS);
+    return dS;
+}
+
+// one regular face of the box kernel (method_viscous is on: the host sends other runs to the slice-class kernel)
+template <bool ROCKS, bool MULTIROCK, bool CAP, bool OWN>
+__device__ __forceinline__ double box_face(const TabLayout& L, const EuTablesDev& t, const MarchCarry& m, double lw1, double lo1,
+                                           double S1, double pc1, int rk1, double2 qg, double T)
+{
+    double cap_coef = 0.0, Tdpc = 0.0;
+    if (CAP) {
+        cap_coef = cap_coefficient<ROCKS, MULTIROCK>(L, t, m.rock0, rk1, m.S0, S1);
+        Tdpc = T*(OWN ? (pc1 - m.pc0) : (m.pc0 - pc1));
+    }
+    if (__all_sync(__activemask(), qg.y == 0.0))           // warp-uniform
+        return face_no_gravity<OWN, CAP>(qg.x, m.lw0, m.lo0, lw1, lo1, cap_coef, Tdpc);
+    return face_regular<OWN, CAP>(qg.x, qg.x, qg.y, m.lw0, m.lo0, lw1, lo1, 1, cap_coef, Tdpc);
+}
+
+// the faces of a cell outside the axis planes (boundary, fault, periodic wrap), from the SELL records: bit j of mask
 template <bool ROCKS, bool MULTIROCK, bool CAP>
+__device__ __forceinline__ double box_record_faces(const TabLayout& L, const EuGridDev& g, const EuTablesDev& t, const EuFastDev& f,
+                                                   const EuStepArgs& a, unsigned mask, int c, const MarchCarry& m)
+{
+    const int2* __restrict__ recp = f.rec + f.slice_base[c >> 5] + (c & 31);
+    double acc = 0.0;
+    while (mask) {
+        const int j = __ffs(mask) - 1;
+        mask &= mask - 1u;
+        const int2 r = recp[j*EU_SLICE];
+        if (r.x == EU_REC_PAD) continue;
+        const bool interior = r.x >= 0;
+        const bool own = !interior || c < r.x;
+        const double2 qg = f.qg[r.y];
+        const double S1 = interior ? a.S_in[r.x] : g.bnd_sat[-2 - r.x];
+        const int rk = (MULTIROCK && interior) ? f.rock8[r.x] : m.rock0;
+        double lw1, lo1;
+        Mob<ROCKS, MULTIROCK>::both(L, t, rk, S1, lw1, lo1);
+        double cap_coef = 0.0, Tdpc = 0.0;
+        if (CAP && interior) {
+            cap_coef = cap_coefficient<ROCKS, MULTIROCK>(L, t, m.rock0, rk, m.S0, S1);
+            const double pc1 = a.pc_in[r.x];
+            Tdpc = f.T[r.y]*(own ? (pc1 - m.pc0) : (m.pc0 - pc1));
+        }
+        acc += face_contribution<CAP>(own, interior, qg.x, qg.x, qg.y, m.lw0, m.lo0, lw1, lo1, 1, a.method_gravity, cap_coef, Tdpc);
+    }
+    return acc;
+}
+
+template <bool ROCKS, bool MULTIROCK, bool CAP, int NS>
 __global__ void __launch_bounds__(256, CAP ? 2 : 3)
 k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUtensorMap mapPc,
            const __grid_constant__ CUtensorMap mapQG, const __grid_constant__ CUtensorMap mapT,
            EuGridDev g, EuTablesDev t, EuFastDev f, EuStepArgs a, EuHaloDev halo, EuBoxDev b, int slice_lo, int tab_bytes)
 {
     TabLayout L;
-    L.nn = t.n_nodes_total; L.nb = t.n_buckets; L.shift = 0;
+    L.nn = t.n_nodes_total; L.nb = t.n_buckets; L.nbd = double(t.n_buckets);
     if (ROCKS) tables_to_smem(t);
     // 128-aligned base of the staging area behind the tables
     const unsigned base_u32 = (smem_u32(eu_smem) + unsigned(tab_bytes) + 127u) & ~127u;
     unsigned char* const base = eu_smem + (base_u32 - smem_u32(eu_smem));
     const int tid = threadIdx.x;
-    const int NS = b.stages;
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) mbar_init(base_u32 + b.off_bar + 8*s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -100,12 +156,10 @@ k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUt
         const unsigned long long key = *a.fail_key;
         if (key != ~0ULL && (unsigned)(key >> 32) < (unsigned)a.substep) return;
     }
+    constexpr int E = CAP ? 32 : 16;                            // bytes per ring entry: {lw, lo} [S, pc]
     const int tx = b.tx, ty = b.ty, txp = tx + 2, txf = tx + 1, txs = tx + 4;      // row lengths: ring / T boxes, face boxes, S boxes
-    const int n_tile = tx*ty;
     const int lx = tid % tx, ly = tid/tx;
-    const bool in_tile = tid < n_tile;
-    const int li = (ly + 1)*txp + lx + 1;                       // own entry in a ring buffer
-    const int ls = (ly + 1)*txs + lx + 2;                       // own entry in an S / pc box
+    const bool in_tile = tid < tx*ty;
     // halo duty: threads 0 .. 2(tx+ty)-1 each own one halo cell of the ring buffers
     int hx = 0, hy = 0;
     bool has_halo = true;
@@ -114,11 +168,19 @@ k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUt
     else if (tid < 2*tx + ty)     { hx = -1;             hy = tid - 2*tx; }
     else if (tid < 2*tx + 2*ty)   { hx = tx;             hy = tid - 2*tx - ty; }
     else has_halo = false;
-    const int hi = (hy + 1)*txp + hx + 1;
-    const int hs = (hy + 1)*txs + hx + 2;
+    // byte offsets of this thread's entries (ring buffers, S / pc boxes, face boxes, T boxes)
+    const int o_ring = ((ly + 1)*txp + lx + 1)*E, o_ring_h = ((hy + 1)*txp + hx + 1)*E;
+    const int o_rk = (ly + 1)*txp + lx + 1, o_rk_h = (hy + 1)*txp + hx + 1;
+    const int o_S = ((ly + 1)*txs + lx + 2)*8, o_S_h = ((hy + 1)*txs + hx + 2)*8;
+    const int o_F = (ly*txf + lx)*16;
+    const int o_T = (ly*txp + lx)*8;
     const int D = b.nx*b.ny;
-    unsigned gb = 0;                                            // bundles consumed by this block so far
     const unsigned bundle_bytes = unsigned(txs*(ty + 2)*8*(CAP ? 2 : 1) + 3*txf*(ty + 1)*16 + (CAP ? 3*txp*(ty + 1)*8 : 0));
+    const unsigned char* const stage0 = base + b.off_stage;
+    unsigned char* const ring0 = base + b.off_lam;
+    unsigned char* const rk0 = base + b.off_rk;
+    int slot = 0;                                               // stage of the current bundle; par = phase parity of its mbarrier
+    unsigned par = 0;
 
     for (int u = blockIdx.x; u < b.n_units; u += gridDim.x) {
         const int4 unit = __ldg(b.units + u);
@@ -136,12 +198,10 @@ k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUt
             __threadfence_system();
         }
         __syncthreads();                                        // every stage and ring buffer of the previous unit is free
-        const unsigned gb0 = gb;                                // number of this unit's first bundle
-        auto issue = [&](int j) {                               // bundle j of this unit: plane k = z0 - 1 + j
-            const int k = z0 - 1 + j;
-            const unsigned slot = (gb0 + unsigned(j)) % unsigned(NS);
-            const unsigned bar = base_u32 + b.off_bar + 8*slot;
-            const unsigned st = base_u32 + b.off_stage + slot*unsigned(b.stage_bytes);
+        // bundle of plane k into stage s
+        auto issue = [&](int k, int s) {
+            const unsigned bar = base_u32 + b.off_bar + 8*s;
+            const unsigned st = base_u32 + b.off_stage + unsigned(s)*unsigned(b.stage_bytes);
             mbar_expect_tx(bar, bundle_bytes);
             tma_load_3d(st + b.off_S, &mapS, x0 - 2, y0 - 1, k + 1, bar);
             if (CAP) tma_load_3d(st + b.off_pc, &mapPc, x0 - 2, y0 - 1, k + 1, bar);
@@ -155,117 +215,114 @@ k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUt
             }
         };
         if (tid == 0) {
-            for (int j = 0; j < NS && j < nb; ++j) issue(j);
+            int s = slot;
+            for (int j = 0; j < NS && j < nb; ++j) { issue(z0 - 1 + j, s); s = (s + 1 == NS) ? 0 : s + 1; }
         }
         // ---- own column: the cell of plane z0-1 (operands of the first carried face)
         const int gx = x0 + lx, gy = y0 + ly;
         const bool active = in_tile && gx < b.nx && gy < b.ny;
-        const int col = gx + b.nx*gy;                           // cell of plane 0 of this column
+        int c = gx + b.nx*gy + (z0 - 1)*D;                      // cell of plane k of this column
         MarchCarry m;
         m.S0 = 0.0; m.pc0 = 0.0; m.rock0 = 0; m.dS4 = 0.0;
         if (active && z0 > 0) {
-            const int c = col + (z0 - 1)*D;
             m.S0 = __ldg(a.S_in + c);
             if (MULTIROCK) m.rock0 = __ldg(f.rock8 + c);
             if (CAP) m.pc0 = __ldg(a.pc_in + c);
         }
         Mob<ROCKS, MULTIROCK>::both(L, t, m.rock0, m.S0, m.lw0, m.lo0);
-        // halo cell: its column index in the grid (or -1 outside), for the rock id
-        int hcol = -1;
-        if (has_halo) {
+        // halo cell: its cell index in plane k (or -1 outside the grid), for the rock id
+        int hc = -1;
+        if (MULTIROCK && has_halo) {
             const int qx = x0 + hx, qy = y0 + hy;
-            if (qx >= 0 && qx < b.nx && qy >= 0 && qy < b.ny) hcol = qx + b.nx*qy;
+            if (qx >= 0 && qx < b.nx && qy >= 0 && qy < b.ny) hc = qx + b.nx*qy + (z0 - 1)*D;
         }
-        for (int j = 0; j < nb; ++j, ++gb) {
-            const int k = z0 - 1 + j;
-            const unsigned slot = gb % unsigned(NS);
-            const unsigned char* st = base + b.off_stage + slot*size_t(b.stage_bytes);
-            mbar_wait(base_u32 + b.off_bar + 8*slot, (gb/unsigned(NS)) & 1u);
-            // ---- phase A: rock curves of plane k+1, once per cell
-            const double* Sn = reinterpret_cast<const double*>(st + b.off_S);
-            const double* Pn = reinterpret_cast<const double*>(st + b.off_pc);
-            double* ring_next = reinterpret_cast<double*>(base + b.off_lam + ((k + 1) % 3)*size_t(b.lam_bytes));
-            unsigned char* rk_next = base + b.off_rk + ((k + 1) % 3)*size_t(b.rk_bytes);
+        // ring buffers: next (plane k+1, written in phase A), cur (plane k, read in phase B), and the one in between
+        int r_next = ((z0 % 3) + 3) % 3, r_cur = (r_next + 2) % 3;
+        for (int k = z0 - 1; k < z1; ++k) {
+            // operands of plane k that are not staged: requested now, used after the barrier
+            double inv_pv = 0.0;
+            unsigned mask = 0u;
+            const bool update = active && k >= z0;
+            if (update) {
+                inv_pv = ldg_f64(f.inv_porevol + c);
+                mask = __ldg(b.cmask + c);
+            }
             const bool up_ok = k + 1 < b.nz;
-            double S1 = 0.0, pc1 = 0.0, lw1, lo1;
-            int rock1 = 0;
+            int rock1 = 0, rock_h = 0;
+            if (MULTIROCK) {
+                if (active && up_ok) rock1 = __ldg(f.rock8 + c + D);
+                if (hc >= 0 && up_ok) rock_h = __ldg(f.rock8 + hc + D);
+            }
+            const unsigned char* st = stage0 + slot*b.stage_bytes;
+            mbar_wait(base_u32 + b.off_bar + 8*slot, par);
+            // ---- phase A: rock curves of plane k+1, once per cell
+            unsigned char* ring_next = ring0 + r_next*b.lam_bytes;
+            double S1 = 0.0, pc1 = 0.0, lw1 = 0.0, lo1 = 0.0;
             if (in_tile) {
-                S1 = Sn[ls];
-                if (MULTIROCK && active && up_ok) rock1 = __ldg(f.rock8 + col + (k + 1)*D);
-                if (CAP) pc1 = Pn[ls];
+                S1 = *reinterpret_cast<const double*>(st + b.off_S + o_S);
+                if (CAP) pc1 = *reinterpret_cast<const double*>(st + b.off_pc + o_S);
                 Mob<ROCKS, MULTIROCK>::both(L, t, rock1, S1, lw1, lo1);
                 if (CAP) {
-                    reinterpret_cast<double4*>(ring_next)[li] = make_double4(lw1, lo1, S1, pc1);
-                    if (MULTIROCK) rk_next[li] = (unsigned char)rock1;
+                    *reinterpret_cast<double4*>(ring_next + o_ring) = make_double4(lw1, lo1, S1, pc1);
+                    if (MULTIROCK) rk0[r_next*b.rk_bytes + o_rk] = (unsigned char)rock1;
                 } else {
-                    reinterpret_cast<double2*>(ring_next)[li] = make_double2(lw1, lo1);
+                    *reinterpret_cast<double2*>(ring_next + o_ring) = make_double2(lw1, lo1);
                 }
             }
             if (has_halo) {
-                const double Sh = Sn[hs];
-                int rh = 0;
-                if (MULTIROCK && hcol >= 0 && up_ok) rh = __ldg(f.rock8 + hcol + (k + 1)*D);
+                const double Sh = *reinterpret_cast<const double*>(st + b.off_S + o_S_h);
                 double lwh, loh;
-                Mob<ROCKS, MULTIROCK>::both(L, t, rh, Sh, lwh, loh);
+                Mob<ROCKS, MULTIROCK>::both(L, t, rock_h, Sh, lwh, loh);
                 if (CAP) {
-                    reinterpret_cast<double4*>(ring_next)[hi] = make_double4(lwh, loh, Sh, Pn[hs]);
-                    if (MULTIROCK) rk_next[hi] = (unsigned char)rh;
+                    const double ph = *reinterpret_cast<const double*>(st + b.off_pc + o_S_h);
+                    *reinterpret_cast<double4*>(ring_next + o_ring_h) = make_double4(lwh, loh, Sh, ph);
+                    if (MULTIROCK) rk0[r_next*b.rk_bytes + o_rk_h] = (unsigned char)rock_h;
                 } else {
-                    reinterpret_cast<double2*>(ring_next)[hi] = make_double2(lwh, loh);
+                    *reinterpret_cast<double2*>(ring_next + o_ring_h) = make_double2(lwh, loh);
                 }
             }
             __syncthreads();
-            // the stage of the previous step is free now: refill it (bundle j - 1 + NS)
-            if (tid == 0 && j >= 1 && j - 1 + NS < nb) issue(j - 1 + NS);
+            // the stage of the previous step is free now: refill it with the bundle NS - 1 planes ahead
+            if (tid == 0 && k >= z0 && k - 1 + NS < z1) issue(k - 1 + NS, slot == 0 ? NS - 1 : slot - 1);
             // ---- phase B: faces of plane k
-            const double2* QG = reinterpret_cast<const double2*>(st + b.off_qg);
-            const double* TT = reinterpret_cast<const double*>(st + b.off_T);
-            const int fz = ly*txf + lx;
-            const size_t qstride = size_t(b.qg_bytes)/16, tstride = size_t(b.T_bytes)/8;
-            const int tz = ly*txp + lx;                           // T boxes have rows of tx+2
-            double2 lam5 = make_double2(lw1, lo1);
             if (in_tile) {
-                const double2 qg5 = QG[2*qstride + fz];
-                const double T5 = CAP ? TT[2*tstride + tz] : 0.0;
-                const double dS5 = regular_slot<ROCKS, MULTIROCK, CAP, true>(L, t, a, m, lam5, S1, rock1, qg5, 1.0, false, T5, pc1);
-                if (active && k >= z0) {
-                    const int c = col + k*D;
-                    const double inv_pv = ldg_f64(f.inv_porevol + c);
-                    const unsigned mask = __ldg(b.cmask + c);
-                    const double* ring = reinterpret_cast<const double*>(base + b.off_lam + (k % 3)*size_t(b.lam_bytes));
-                    const unsigned char* rk = base + b.off_rk + (k % 3)*size_t(b.rk_bytes);
+                const unsigned char* QG = st + b.off_qg + o_F;
+                const unsigned char* TT = st + b.off_T + o_T;
+                const double2 qg5 = *reinterpret_cast<const double2*>(QG + 2*b.qg_bytes);
+                const double T5 = CAP ? *reinterpret_cast<const double*>(TT + 2*b.T_bytes) : 0.0;
+                const double dS5 = box_face<ROCKS, MULTIROCK, CAP, true>(L, t, m, lw1, lo1, S1, pc1, rock1, qg5, T5);
+                if (update) {
+                    const unsigned char* ring = ring0 + r_cur*b.lam_bytes + o_ring;
+                    const unsigned char* rk = rk0 + r_cur*b.rk_bytes + o_rk;
                     double acc = m.dS4 - dS5;
-                    // lateral faces: slot order x-, x+, y-, y+
-                    const int nbi[4] = { li - 1, li + 1, li - txp, li + txp };
-                    const int qi[4] = { fz, fz + 1, int(qstride) + fz, int(qstride) + fz + txf };
-                    const int ti[4] = { tz + 1, tz + 2, int(tstride) + tz, int(tstride) + tz + txp };   // (x box starts at x0 - 2)
-                    double2 lam[4], qg[4];
-                    double Sx[4], Px[4], Tx[4];
+                    // lateral faces x-, x+, y-, y+: neighbour entry, face pair, T
+                    const int dr[4] = { -E, E, -txp*E, txp*E };
+                    const int dk[4] = { -1, 1, -txp, txp };
+                    const int dq[4] = { 0, 16, b.qg_bytes, b.qg_bytes + txf*16 };
+                    const int dt[4] = { 8, 16, b.T_bytes, b.T_bytes + txp*8 };
+                    double lwn[4], lon[4], Sx[4], Px[4], Tx[4];
+                    double2 qg[4];
                     int rx[4];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         if (CAP) {
-                            const double4 e = reinterpret_cast<const double4*>(ring)[nbi[q]];
-                            lam[q] = make_double2(e.x, e.y); Sx[q] = e.z; Px[q] = e.w;
-                            rx[q] = MULTIROCK ? int(rk[nbi[q]]) : 0;
-                            Tx[q] = TT[ti[q]];
+                            const double4 e = *reinterpret_cast<const double4*>(ring + dr[q]);
+                            lwn[q] = e.x; lon[q] = e.y; Sx[q] = e.z; Px[q] = e.w;
+                            rx[q] = MULTIROCK ? int(rk[dk[q]]) : 0;
+                            Tx[q] = *reinterpret_cast<const double*>(TT + dt[q]);
                         } else {
-                            lam[q] = reinterpret_cast<const double2*>(ring)[nbi[q]];
-                            Sx[q] = 0.0; Px[q] = 0.0; Tx[q] = 0.0; rx[q] = 0;
+                            const double2 e = *reinterpret_cast<const double2*>(ring + dr[q]);
+                            lwn[q] = e.x; lon[q] = e.y; Sx[q] = 0.0; Px[q] = 0.0; Tx[q] = 0.0; rx[q] = 0;
                         }
-                        qg[q] = QG[qi[q]];
+                        qg[q] = *reinterpret_cast<const double2*>(QG + dq[q]);
                     }
-                    acc += regular_slot<ROCKS, MULTIROCK, CAP, false>(L, t, a, m, lam[0], Sx[0], rx[0], qg[0], 1.0, false, Tx[0], Px[0]);
-                    acc -= regular_slot<ROCKS, MULTIROCK, CAP, true>(L, t, a, m, lam[1], Sx[1], rx[1], qg[1], 1.0, false, Tx[1], Px[1]);
-                    acc += regular_slot<ROCKS, MULTIROCK, CAP, false>(L, t, a, m, lam[2], Sx[2], rx[2], qg[2], 1.0, false, Tx[2], Px[2]);
-                    acc -= regular_slot<ROCKS, MULTIROCK, CAP, true>(L, t, a, m, lam[3], Sx[3], rx[3], qg[3], 1.0, false, Tx[3], Px[3]);
+                    acc += box_face<ROCKS, MULTIROCK, CAP, false>(L, t, m, lwn[0], lon[0], Sx[0], Px[0], rx[0], qg[0], Tx[0]);
+                    acc -= box_face<ROCKS, MULTIROCK, CAP, true>(L, t, m, lwn[1], lon[1], Sx[1], Px[1], rx[1], qg[1], Tx[1]);
+                    acc += box_face<ROCKS, MULTIROCK, CAP, false>(L, t, m, lwn[2], lon[2], Sx[2], Px[2], rx[2], qg[2], Tx[2]);
+                    acc -= box_face<ROCKS, MULTIROCK, CAP, true>(L, t, m, lwn[3], lon[3], Sx[3], Px[3], rx[3], qg[3], Tx[3]);
+                    if (mask) acc += box_record_faces<ROCKS, MULTIROCK, CAP>(L, g, t, f, a, mask, c, m);
                     OwnMob<false> own0;
                     own0.lw[0] = m.lw0; own0.lo[0] = m.lo0;
-                    if (mask) {                                 // boundary / fault / periodic faces of this cell
-                        const int base_rec = f.slice_base[c >> 5];
-                        acc += gather_cell_loop<ROCKS, MULTIROCK, CAP, false, false>(L, g, t, f, a, f.rec + base_rec + (c & 31),
-                                                                                     32 - __clz(mask), mask, c, m.S0, m.rock0, m.pc0, own0);
-                    }
                     double pcn;
                     const double sat = finish_cell<ROCKS, MULTIROCK, CAP, false>(L, t, f, a, c, m.S0, m.rock0, own0, inv_pv, acc, pcn);
                     if (range >= 0) {
@@ -280,6 +337,12 @@ k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUt
                 m.dS4 = dS5;
             }
             m.S0 = S1; m.lw0 = lw1; m.lo0 = lo1; m.rock0 = rock1; m.pc0 = pc1;
+            c += D;
+            if (MULTIROCK && hc >= 0) hc += D;
+            ++slot;
+            if (slot == NS) { slot = 0; par ^= 1u; }
+            r_cur = r_next;
+            r_next = (r_next == 2) ? 0 : r_next + 1;
         }
         if (range >= 0) {
             // all pushes of this unit, one system-scope fence, then the finished-unit counter of the range

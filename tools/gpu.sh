@@ -17,9 +17,9 @@ perf)     for c in "c2 --n 100" "c2 --n 200" "c2b --n 100" "c3" "t3 --n 100"; do
             n=$(echo $c | tr -d ' -'); ( timeout 400 python tools/perf_case.py $c --check-strict > $O/perf_$n.json 2> $O/perf_$n.err ); cat $O/perf_$n.json; done ;;
 launches) timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_VG_8M.csv \
             python bench.py --steps 1 --warmup 1 --substeps 10 --nz 32 --no-cpu --no-e2e --no-configs > $O/launches_bench.log 2>&1 ;;
-ncu)      timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_ -s 8 -c 1 -f -o $O/fast_VG_8M \
+ncu)      timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_box_step|k_fast_step" -s 5 -c 1 -f -o $O/fast_VG_8M \
             python bench.py --steps 1 --warmup 1 --substeps 10 --nz 32 --no-cpu --no-e2e --no-configs > $O/ncu_full.log 2>&1 ;;
-ncu_cap)  timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_ -s 8 -c 1 -f -o $O/fast_VGC_8M \
+ncu_cap)  timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_box_step|k_fast_step" -s 5 -c 1 -f -o $O/fast_VGC_8M \
             python bench.py --steps 1 --warmup 1 --substeps 10 --nz 32 --capillary --no-cpu --no-e2e --no-configs > $O/ncu_full_cap.log 2>&1 ;;
 sanitize) for tool in memcheck racecheck synccheck; do
             ( timeout 400 compute-sanitizer --tool $tool --error-exitcode 7 python -m pytest tests/test_gpu_parity.py -m gpu -x -q \
