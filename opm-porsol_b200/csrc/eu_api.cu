@@ -116,6 +116,8 @@ struct eu_solver {
     bool ran_box = false;              // the last FAST substep ran the box kernel
     int box_enabled = 1;               // EU_BOX=0 keeps the slice-class kernel (tuning / A-B knob)
     DevBuf<unsigned short> d_cmask;    // per cell: record slots holding faces outside the axis planes
+    DevBuf<int> d_irr_cells;           // own cells with such faces (work list of k_box_irregular)
+    DevBuf<double> d_acc_irr;          // per cell: their summed contribution in the current substep
     int n_slices = 0;
     bool use_nn = false;
     int prefetch = 1;                  // EU_PREFETCH=<march steps ahead>, 0 turns the L2 prefetch of the marches off (tuning knob)
@@ -1334,10 +1336,17 @@ int eu_grid_end(eu_handle h)
     if (h->mode == EU_MODE_FAST && !h->tensor_fast && h->box_ok && h->box_enabled && h->max_slots <= 16 && h->cfg.world_size <= 1) {
         // box kernel: per-cell mask of the faces outside the axis planes, tensor maps over the state and face arrays
         EU_CUDA(h, h->d_cmask.alloc(n));
-        eu_launch_cell_mask(h->grid(), h->d_slice_base.p, h->d_rec.p, h->d_cmask.p, h->st);
+        EU_CUDA(h, h->d_irr_cells.alloc(n));
+        EU_CUDA(h, h->d_acc_irr.alloc(n));
+        EU_CUDA(h, cudaMemsetAsync(h->d_acc_irr.p, 0, n*sizeof(double), h->st));
+        EU_CUDA(h, cudaMemsetAsync(h->d_flags.p, 0, 4*sizeof(int), h->st));
+        eu_launch_cell_mask(h->grid(), h->d_slice_base.p, h->d_rec.p, h->d_cmask.p, h->d_irr_cells.p, h->d_flags.p, h->st);
+        int n_irr = 0;
+        EU_CUDA(h, cudaMemcpyAsync(&n_irr, h->d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+        EU_CUDA(h, cudaStreamSynchronize(h->st));
         const int nx = h->axis[1], ny = h->axis[2]/h->axis[1], nz = h->n_local/h->axis[2];
         h->box = eu_box_plan_create(nx, ny, nz, h->own_lo/h->axis[2], h->own_hi/h->axis[2], h->d_S[0].p, h->d_S[1].p, h->d_pc[0].p,
-                                    h->d_pc[1].p, h->d_qg.p, h->d_T.p, h->d_cmask.p, h->n_sms);
+                                    h->d_pc[1].p, h->d_qg.p, h->d_T.p, h->d_cmask.p, h->d_irr_cells.p, n_irr, h->d_acc_irr.p, h->n_sms);
     }
     EU_CUDA(h, cudaStreamSynchronize(h->st));
     EU_CUDA(h, cudaGetLastError());

@@ -934,6 +934,9 @@ struct EuBoxPlan {
     int n_units = 0, n_bnd_units[2] = { 0, 0 };
     int units_key[5] = { -1, -1, -1, -1, -1 };      // (bnd planes lo, hi, grid blocks, lz override, cap) the unit list was built for
     const unsigned short* cmask = nullptr;
+    const int* irr_cells = nullptr;
+    int n_irr = 0;
+    double* acc_irr = nullptr;
     int n_sms = 148;
 };
 
@@ -1009,19 +1012,19 @@ void eu_box_plan_destroy(EuBoxPlan* p)
 
 // nullptr when the box kernel does not apply (then the slice-class kernel runs)
 EuBoxPlan* eu_box_plan_create(int nx, int ny, int nz, int z_lo, int z_hi, double* S0, double* S1, double* pc0, double* pc1,
-                              double2* qg, double* T, const unsigned short* cmask, int n_sms)
+                              double2* qg, double* T, const unsigned short* cmask, const int* irr_cells, int n_irr, double* acc_irr, int n_sms)
 {
     // TMA: global strides are multiples of 16 bytes (nx even); coordinates fit the unit encoding
     if (nx < 2 || (nx & 1) || ny < 1 || nz < 1 || nx > 65535 || ny > 32767) return nullptr;
     if (!encode_tiled_fn()) return nullptr;
     EuBoxPlan* p = new EuBoxPlan;
     p->nx = nx; p->ny = ny; p->nz = nz; p->z_lo = z_lo; p->z_hi = z_hi; p->n_local = nx*ny*nz;
-    p->cmask = cmask; p->n_sms = n_sms;
+    p->cmask = cmask; p->irr_cells = irr_cells; p->n_irr = n_irr; p->acc_irr = acc_irr; p->n_sms = n_sms;
     // tile: tx even, 2(tx+1) <= 256 (TMA box limit), tx*ty <= 256 threads; minimise (halo overhead) x (idle threads)
     {
-        const char* e = getenv("EU_BOX_TILE");          // "tx,ty" (tuning knob)
+        const char* e = getenv("EU_BOX_TILE");          // "<tx>x<ty>" (tuning knob)
         int etx = 0, ety = 0;
-        if (e && std::sscanf(e, "%d,%d", &etx, &ety) == 2 && etx >= 2 && !(etx & 1) && etx <= 126 && ety >= 1 && etx*ety <= 256) {
+        if (e && std::sscanf(e, "%dx%d", &etx, &ety) == 2 && etx >= 2 && !(etx & 1) && etx <= 126 && ety >= 1 && etx*ety <= 256) {
             p->tx = etx; p->ty = ety;
         } else {
             double best = 1e300;
@@ -1127,13 +1130,24 @@ static int launch_box(EuBoxPlan* p, const EuGridDev& g, const EuTablesDev& t, co
     static int stages_env = -1;
     if (stages_env < 0) { const char* e = getenv("EU_BOX_STAGES"); stages_env = e ? std::min(std::max(atoi(e), 2), 4) : 0; }
     // as many bundles in flight (2..4) as still leave the kernel's resident blocks per SM (3, or 2 with the capillary term)
-    const int want_blocks = CAP ? 2 : 3;
+    static int minb_pre = -1;
+    if (minb_pre < 0) { const char* e = getenv("EU_BOX_MINB"); minb_pre = e ? atoi(e) : 0; }
+    const int want_blocks = minb_pre ? minb_pre : (CAP ? 2 : 3);
     int stages = stages_env ? stages_env : 3;
     BoxLayout lay = box_layout(*p, CAP, MULTIROCK, stages, tab_bytes);
     const size_t budget = size_t(227*1024)/want_blocks - 1024;
     while (!stages_env && stages > 2 && lay.total > budget) lay = box_layout(*p, CAP, MULTIROCK, --stages, tab_bytes);
-    auto kern = stages == 2 ? k_box_step<ROCKS, MULTIROCK, CAP, 2> : (stages == 3 ? k_box_step<ROCKS, MULTIROCK, CAP, 3> : k_box_step<ROCKS, MULTIROCK, CAP, 4>);
-    static size_t smem_set[5] = { 0, 0, 0, 0, 0 };
+    // EU_BOX_MINB (tuning knob): resident blocks per SM the kernel is compiled for (register budget 2: 128, 3: 80)
+    static int minb_env = -1;
+    if (minb_env < 0) { const char* e = getenv("EU_BOX_MINB"); minb_env = e ? atoi(e) : 0; }
+    const bool two = minb_env ? minb_env == 2 : CAP;
+    auto kern3 = stages == 2 ? k_box_step<ROCKS, MULTIROCK, CAP, 2, 3> : (stages == 3 ? k_box_step<ROCKS, MULTIROCK, CAP, 3, 3> : k_box_step<ROCKS, MULTIROCK, CAP, 4, 3>);
+    auto kern2 = stages == 2 ? k_box_step<ROCKS, MULTIROCK, CAP, 2, 2> : (stages == 3 ? k_box_step<ROCKS, MULTIROCK, CAP, 3, 2> : k_box_step<ROCKS, MULTIROCK, CAP, 4, 2>);
+    auto kern4 = stages == 2 ? k_box_step<ROCKS, MULTIROCK, CAP, 2, 4> : k_box_step<ROCKS, MULTIROCK, CAP, 3, 4>;
+    auto kern = minb_env == 4 ? kern4 : (two ? kern2 : kern3);
+    static size_t smem_set_all[2][5] = { { 0, 0, 0, 0, 0 }, { 0, 0, 0, 0, 0 } };
+    static size_t smem_set4[5] = { 0, 0, 0, 0, 0 };
+    size_t* smem_set = minb_env == 4 ? smem_set4 : smem_set_all[two ? 1 : 0];
     if (lay.total > smem_set[stages]) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total) != cudaSuccess) return -1;
         smem_set[stages] = lay.total;
@@ -1147,9 +1161,17 @@ static int launch_box(EuBoxPlan* p, const EuGridDev& g, const EuTablesDev& t, co
     lay.b.units = p->d_units;
     lay.b.n_units = p->n_units;
     lay.b.cmask = p->cmask;
+    lay.b.acc_irr = p->acc_irr;
+    int launches = 1;
+    if (p->n_irr > 0) {
+        // pre-pass: faces outside the axis planes, summed per cell
+        const int ib = std::min((p->n_irr + 255)/256, p->n_sms*8);
+        k_box_irregular<ROCKS, MULTIROCK, CAP><<<ib, 256, tab_bytes, st>>>(g, t, f, a, halo, p->irr_cells, p->n_irr, p->cmask, p->acc_irr);
+        ++launches;
+    }
     const int blocks = std::min(grid_full, p->n_units);
     kern<<<blocks, p->threads, lay.total, st>>>(p->mapS[cur], p->mapPc[cur], p->mapQG, p->mapT, g, t, f, a, halo, lay.b, slice_lo, (int)tab_bytes);
-    return 1;
+    return launches;
 }
 
 // one substep of the own planes [z_lo, z_hi) with the box kernel; returns the number of launches, -1 on error

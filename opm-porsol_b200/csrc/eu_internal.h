@@ -185,7 +185,8 @@ void eu_launch_assign_fid(const EuGridDev& g, const int* owner_hf, const unsigne
                           int* fid_of_hf, cudaStream_t st);
 // votes for candidate positive neighbour offsets (n_cand <= 16): how many interior faces have neighbour = cell + cand[q]
 void eu_launch_offset_votes(const EuGridDev& g, const int* cand, int n_cand, unsigned long long* votes, cudaStream_t st);
-void eu_launch_cell_mask(const EuGridDev& g, const int* slice_base, const int2* rec, unsigned short* cmask, cudaStream_t st);
+void eu_launch_cell_mask(const EuGridDev& g, const int* slice_base, const int2* rec, unsigned short* cmask, int* list, int* count,
+                         cudaStream_t st);
 void eu_launch_build_records(const EuGridDev& g, const int* owner_hf, const int* fid_of_hf, const unsigned char* slot_of_hf,
                              const int* slice_base, int2* rec, int2* desc, int* n_regular_slots, cudaStream_t st);
 void eu_launch_contract(const EuGridDev& g, const EuTablesDev& t, const int* owner_hf, const int* fid_of_hf,
@@ -231,7 +232,7 @@ size_t eu_fast_smem_bytes(const EuTablesDev& t);
 // box kernel (eu_tile.cuh): plane sweep over tiles with TMA-staged operands, for local numberings that are a box
 struct EuBoxPlan;
 EuBoxPlan* eu_box_plan_create(int nx, int ny, int nz, int z_lo, int z_hi, double* S0, double* S1, double* pc0, double* pc1,
-                              double2* qg, double* T, const unsigned short* cmask, int n_sms);
+                              double2* qg, double* T, const unsigned short* cmask, const int* irr_cells, int n_irr, double* acc_irr, int n_sms);
 void eu_box_plan_destroy(EuBoxPlan* p);
 void eu_box_plan_info(const EuBoxPlan* p, int out[6]);      // tile x, tile y, units, boundary units A, B, threads per block
 int eu_launch_box_step(EuBoxPlan* p, const EuGridDev& g, const EuTablesDev& t, const EuFastDev& f, const EuStepArgs& a,

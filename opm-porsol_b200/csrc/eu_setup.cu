@@ -282,8 +282,9 @@ __global__ void k_assign_fid(EuGridDev g, const int* __restrict__ owner_hf, cons
 
 // per cell: which record slots (SELL slot j < 16) hold a face that is NOT in an axis plane -- the faces the box kernel
 // adds one by one from the records after its regular faces
+// The own cells with a non-zero mask are appended to `list` (their number to *count): the work list of k_box_irregular.
 __global__ void k_cell_mask(EuGridDev g, const int* __restrict__ slice_base, const int2* __restrict__ rec,
-                            unsigned short* __restrict__ cmask)
+                            unsigned short* __restrict__ cmask, int* __restrict__ list, int* __restrict__ count)
 {
     const int c = blockIdx.x*blockDim.x + threadIdx.x;
     if (c >= g.n_local) return;
@@ -296,6 +297,17 @@ __global__ void k_cell_mask(EuGridDev g, const int* __restrict__ slice_base, con
         if (r.x != EU_REC_PAD && r.y >= 3*g.n_local) m |= 1u << j;
     }
     cmask[c] = (unsigned short)m;
+    // warp-aggregated append (ascending within a warp; the order across warps does not matter)
+    const bool mine = m != 0u && c >= g.own_lo && c < g.own_hi;
+    const unsigned act = __activemask();
+    const unsigned vote = __ballot_sync(act, mine);
+    if (vote) {
+        const int leader = __ffs(vote) - 1;
+        int start = 0;
+        if ((threadIdx.x & 31) == leader) start = atomicAdd(count, __popc(vote));
+        start = __shfl_sync(act, start, leader);
+        if (mine) list[start + __popc(vote & ((1u << (threadIdx.x & 31)) - 1u))] = c;
+    }
 }
 
 __global__ void k_build_records(EuGridDev g, const int* __restrict__ owner_hf, const int* __restrict__ fid_of_hf,
@@ -890,9 +902,10 @@ void eu_launch_offset_votes(const EuGridDev& g, const int* cand, int n_cand, uns
 {
     k_offset_votes<<<div_up(g.n_local, kThreads), kThreads, 0, st>>>(g, cand, n_cand, votes);
 }
-void eu_launch_cell_mask(const EuGridDev& g, const int* slice_base, const int2* rec, unsigned short* cmask, cudaStream_t st)
+void eu_launch_cell_mask(const EuGridDev& g, const int* slice_base, const int2* rec, unsigned short* cmask, int* list, int* count,
+                         cudaStream_t st)
 {
-    k_cell_mask<<<div_up(g.n_local, kThreads), kThreads, 0, st>>>(g, slice_base, rec, cmask);
+    k_cell_mask<<<div_up(g.n_local, kThreads), kThreads, 0, st>>>(g, slice_base, rec, cmask, list, count);
 }
 void eu_launch_build_records(const EuGridDev& g, const int* owner_hf, const int* fid_of_hf, const unsigned char* slot_of_hf,
                              const int* slice_base, int2* rec, int2* desc, int* n_regular_slots, cudaStream_t st)

@@ -38,7 +38,8 @@ struct EuBoxDev {
     int lam_bytes, rk_bytes, stage_bytes;
     int off_S, off_pc, off_qg, off_T;             // inside a stage
     int qg_bytes, T_bytes;                        // one axis' box
-    const unsigned short* cmask;
+    const unsigned short* cmask;  // per cell: record slots with faces outside the axis planes
+    const double* acc_irr;        // per cell with a non-zero mask: sum of those faces' contributions (k_box_irregular)
 };
 
 namespace {
@@ -133,8 +134,43 @@ __device__ __forceinline__ double box_record_faces(const TabLayout& L, const EuG
     return acc;
 }
 
-template <bool ROCKS, bool MULTIROCK, bool CAP, int NS>
-__global__ void __launch_bounds__(256, CAP ? 2 : 3)
+// Pre-pass of a substep in box mode: the faces outside the axis planes (boundary, fault, periodic wrap), one thread per
+// cell that has any (compact list built at upload).  Writes the sum of their contributions to the cell's residual;
+// k_box_step adds it to the regular faces.  A few per cent of the cells: taking these faces out of the sweep keeps
+// the sweep's warps in step (a single lane with a boundary face used to hold back its whole block at the barrier).
+template <bool ROCKS, bool MULTIROCK, bool CAP>
+__global__ void __launch_bounds__(256) k_box_irregular(EuGridDev g, EuTablesDev t, EuFastDev f, EuStepArgs a, EuHaloDev halo,
+                                                       const int* __restrict__ cells, int n, const unsigned short* __restrict__ cmask,
+                                                       double* __restrict__ acc_irr)
+{
+    TabLayout L;
+    L.nn = t.n_nodes_total; L.nb = t.n_buckets; L.nbd = double(t.n_buckets);
+    if (ROCKS) tables_to_smem(t);
+    if (halo.enabled && threadIdx.x < halo.n_wait) {
+        // some of these faces may look at ghost cells: the previous substep's pushes must have landed
+        const volatile unsigned* fl = halo.my_flags + halo.wait_rank[threadIdx.x];
+        const long long t0 = clock64();
+        while ((int)(*fl - (halo.epoch - 1u)) < 0) {
+            __nanosleep(100);
+            if (clock64() - t0 > halo.timeout_cycles) { atomicExch(halo.err_flag, 1); break; }
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    for (int i = blockIdx.x*blockDim.x + threadIdx.x; i < n; i += gridDim.x*blockDim.x) {
+        const int c = __ldg(cells + i);
+        MarchCarry m;
+        m.S0 = a.S_in[c];
+        m.rock0 = MULTIROCK ? f.rock8[c] : 0;
+        m.pc0 = CAP ? a.pc_in[c] : 0.0;
+        m.dS4 = 0.0;
+        Mob<ROCKS, MULTIROCK>::both(L, t, m.rock0, m.S0, m.lw0, m.lo0);
+        acc_irr[c] = box_record_faces<ROCKS, MULTIROCK, CAP>(L, g, t, f, a, unsigned(__ldg(cmask + c)), c, m);
+    }
+}
+
+template <bool ROCKS, bool MULTIROCK, bool CAP, int NS, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUtensorMap mapPc,
            const __grid_constant__ CUtensorMap mapQG, const __grid_constant__ CUtensorMap mapT,
            EuGridDev g, EuTablesDev t, EuFastDev f, EuStepArgs a, EuHaloDev halo, EuBoxDev b, int slice_lo, int tab_bytes)
@@ -236,17 +272,20 @@ k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUt
             const int qx = x0 + hx, qy = y0 + hy;
             if (qx >= 0 && qx < b.nx && qy >= 0 && qy < b.ny) hc = qx + b.nx*qy + (z0 - 1)*D;
         }
+        unsigned mk = 0u;                                       // mask of the faces outside the axis planes, plane k (none for z0-1)
         // ring buffers: next (plane k+1, written in phase A), cur (plane k, read in phase B), and the one in between
         int r_next = ((z0 % 3) + 3) % 3, r_cur = (r_next + 2) % 3;
         for (int k = z0 - 1; k < z1; ++k) {
             // operands of plane k that are not staged: requested now, used after the barrier
             double inv_pv = 0.0;
-            unsigned mask = 0u;
             const bool update = active && k >= z0;
-            if (update) {
-                inv_pv = ldg_f64(f.inv_porevol + c);
-                mask = __ldg(b.cmask + c);
-            }
+            if (update) inv_pv = ldg_f64(f.inv_porevol + c);
+            // faces outside the axis planes were summed per cell by k_box_irregular before this launch; the mask of a
+            // plane is fetched one step ahead so that the load of the sum need not wait for it
+            const unsigned mask = mk;
+            double acc_irr = 0.0;
+            if (mask) acc_irr = ldg_f64(b.acc_irr + c);
+            mk = (active && k + 1 < z1) ? unsigned(__ldg(b.cmask + c + D)) : 0u;
             const bool up_ok = k + 1 < b.nz;
             int rock1 = 0, rock_h = 0;
             if (MULTIROCK) {
@@ -320,7 +359,7 @@ k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUt
                     acc -= box_face<ROCKS, MULTIROCK, CAP, true>(L, t, m, lwn[1], lon[1], Sx[1], Px[1], rx[1], qg[1], Tx[1]);
                     acc += box_face<ROCKS, MULTIROCK, CAP, false>(L, t, m, lwn[2], lon[2], Sx[2], Px[2], rx[2], qg[2], Tx[2]);
                     acc -= box_face<ROCKS, MULTIROCK, CAP, true>(L, t, m, lwn[3], lon[3], Sx[3], Px[3], rx[3], qg[3], Tx[3]);
-                    if (mask) acc += box_record_faces<ROCKS, MULTIROCK, CAP>(L, g, t, f, a, mask, c, m);
+                    acc += acc_irr;
                     OwnMob<false> own0;
                     own0.lw[0] = m.lw0; own0.lo[0] = m.lo0;
                     double pcn;
