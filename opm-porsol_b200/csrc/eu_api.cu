@@ -160,6 +160,7 @@ struct eu_solver {
     // fused exchange (FAST mode): boundary slice ranges at the two ends of the own range
     bool fused_ok = false;
     int fused_a_hi = 0, fused_b_lo = 0;
+    int fused_down_max = -1, fused_up_min = INT_MAX;       // extreme local cells of the two boundary ranges
     int fused_peer[2] = { -1, -1 };        // index into peers
     unsigned fused_total[2] = { 0, 0 };
     DevBuf<int> d_fused_dst[2];
@@ -702,23 +703,21 @@ int launch_substep(eu_handle h, const EuStepArgs& a, bool exchange)
         eu_launch_fast_step_t3(g, h->tabf, h->fast(), a, h->own_lo/EU_SLICE, (h->own_hi + EU_SLICE - 1)/EU_SLICE, h->n_sms, h->st);
         return 1;
     }
-    if (h->mode == EU_MODE_FAST && h->box && !h->use_nn && a.method_viscous) {      // (the box kernel has the viscous term built in)
-        // box numbering: plane sweep over tiles with TMA-staged operands (eu_tile.cuh)
-        EuHaloDev halo;
-        std::memset(&halo, 0, sizeof(halo));
-        const int nl = eu_launch_box_step(h->box, g, h->tabf, h->fast(), a, halo, h->cur, h->own_lo/EU_SLICE, 0, 0, h->st);
-        h->ran_box = nl >= 0;
-        return nl < 0 ? -1 : nl;
-    }
     if (h->mode == EU_MODE_FAST) {
-        h->ran_box = false;
         const int slice_lo = h->own_lo/EU_SLICE;
         const int slice_hi = (h->own_hi + EU_SLICE - 1)/EU_SLICE;
         EuHaloDev halo;
         std::memset(&halo, 0, sizeof(halo));
         const bool fused = exchange && fused_halo(h);
-        // the items cover the slices that are not handled as slab-boundary ranges
-        if (build_items(h, fused ? h->fused_a_hi : slice_lo, fused ? h->fused_b_lo : slice_hi) != EU_OK) return -1;
+        bool box = h->box && !h->use_nn && a.method_viscous;             // (the box kernel has the viscous term built in)
+        int bnd_lo = 0, bnd_hi = 0, box_info[6] = { 0, 0, 0, 0, 0, 0 };
+        if (box && fused) {
+            // own planes that hold cells a neighbour rank keeps as ghosts, or that read ghosts
+            const int D = h->axis[2];
+            if (h->fused_down_max >= 0) bnd_lo = (h->fused_down_max - h->own_lo)/D + 1;
+            if (h->fused_up_min < INT_MAX) bnd_hi = (h->own_hi - 1 - h->fused_up_min)/D + 1;
+            if (eu_box_plan_units(h->box, bnd_lo, bnd_hi, a.method_capillary != 0, box_info)) box = false;      // slab too thin
+        }
         if (fused) {
             const int out = h->cur ^ 1;
             halo.enabled = 1;
@@ -745,6 +744,23 @@ int launch_substep(eu_handle h, const EuStepArgs& a, bool exchange)
             halo.timeout_cycles = 20000000000LL;
             halo.err_flag = h->d_flags.p + 3;
         }
+        if (box) {
+            // box numbering: plane sweep over tiles with TMA-staged operands (eu_tile.cuh).  With the fused exchange the
+            // own planes that hold cells a neighbour rank keeps as ghosts (or that read ghosts) are swept first, as
+            // short work units of their own, and pushed; the kernel counts finished units instead of slices.
+            if (fused) {
+                const unsigned nA = unsigned(box_info[3]), nB = unsigned(box_info[4]);
+                const bool same_peer = h->fused_peer[0] >= 0 && h->fused_peer[0] == h->fused_peer[1];
+                halo.total[0] = same_peer ? nA + nB : (h->fused_peer[0] >= 0 ? nA : 0xffffffffu);
+                halo.total[1] = same_peer ? nA + nB : (h->fused_peer[1] >= 0 ? nB : 0xffffffffu);
+            }
+            const int nl = eu_launch_box_step(h->box, g, h->tabf, h->fast(), a, halo, h->cur, slice_lo, slice_hi, bnd_lo, bnd_hi, h->st);
+            h->ran_box = nl >= 0;
+            return nl < 0 ? -1 : nl;
+        }
+        h->ran_box = false;
+        // the items cover the slices that are not handled as slab-boundary ranges
+        if (build_items(h, fused ? h->fused_a_hi : slice_lo, fused ? h->fused_b_lo : slice_hi) != EU_OK) return -1;
         eu_launch_fast_step(g, h->tabf, h->fast(), a, halo, slice_lo, slice_hi, h->n_sms, h->st);
         return 1;
     }
@@ -1333,7 +1349,7 @@ int eu_grid_end(eu_handle h)
     EU_CUDA(h, h->d_residual.alloc(n));
     EU_CUDA(h, h->d_block_min.alloc(size_t(eu_cfl_blocks(h->n_local))));
     EU_CUDA(h, h->d_fail_key.alloc(1));
-    if (h->mode == EU_MODE_FAST && !h->tensor_fast && h->box_ok && h->box_enabled && h->max_slots <= 16 && h->cfg.world_size <= 1) {
+    if (h->mode == EU_MODE_FAST && !h->tensor_fast && h->box_ok && h->box_enabled && h->max_slots <= 16) {
         // box kernel: per-cell mask of the faces outside the axis planes, tensor maps over the state and face arrays
         EU_CUDA(h, h->d_cmask.alloc(n));
         EU_CUDA(h, h->d_irr_cells.alloc(n));
@@ -1685,7 +1701,7 @@ int eu_transport_solve_resident(eu_handle h, double time, const double gravity[3
             ++launches;
         }
         const int start = h->cur;
-        if (h->mode == EU_MODE_FAST) {       // work items of the substep kernel (built once per grid / decomposition)
+        if (h->mode == EU_MODE_FAST && !(h->box && !h->use_nn && p.method_viscous)) {       // work items of the slice-class kernel (built once per grid / decomposition)
             const bool fused = fused_halo(h);
             if ((rc = build_items(h, fused ? h->fused_a_hi : h->own_lo/EU_SLICE,
                                   fused ? h->fused_b_lo : (h->own_hi + EU_SLICE - 1)/EU_SLICE))) return rc;
@@ -1953,6 +1969,7 @@ int eu_comm_connect(eu_handle h, int n_blobs, const void* const* blobs, const in
             EU_CUDA(h, cudaMemset(h->d_fused_dummy.p, 0, 2*sizeof(unsigned)));
             const unsigned nA = unsigned(a_hi - slice_lo), nB = unsigned(slice_hi - b_lo);
             h->fused_a_hi = a_hi; h->fused_b_lo = b_lo;
+            h->fused_down_max = down_max; h->fused_up_min = up_min;
             h->fused_peer[0] = range_peer[0]; h->fused_peer[1] = range_peer[1];
             if (range_peer[0] >= 0 && range_peer[0] == range_peer[1]) {
                 h->fused_total[0] = h->fused_total[1] = nA + nB;       // one neighbour on both sides (periodic, 2 ranks)

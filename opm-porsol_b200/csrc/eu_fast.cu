@@ -1103,9 +1103,10 @@ static int box_build_units(EuBoxPlan* p, int bnd_lo, int bnd_hi, int grid_blocks
             for (int txi = 0; txi < tiles_x; ++txi)
                 units.push_back(make_int4((txi*p->tx) | ((tyi*p->ty) << 16), z0, z1, flags));
     };
+    // (the caller guarantees bnd_lo + bnd_hi <= own planes: eu_box_plan_units)
     p->n_bnd_units[0] = p->n_bnd_units[1] = 0;
-    if (bnd_lo > 0) { add(p->z_lo, std::min(p->z_lo + bnd_lo, p->z_hi), 1); p->n_bnd_units[0] = tiles; }
-    if (bnd_hi > 0 && zi1 >= zi0) { add(std::max(zi1, p->z_lo + bnd_lo), p->z_hi, 2); p->n_bnd_units[1] = tiles; }
+    if (bnd_lo > 0) { add(p->z_lo, zi0, 1); p->n_bnd_units[0] = tiles; }
+    if (bnd_hi > 0) { add(zi1, p->z_hi, 2); p->n_bnd_units[1] = tiles; }
     if (zi1 > zi0) {
         const int chunks = (zi1 - zi0 + lz - 1)/lz;
         for (int q = 0; q < chunks; ++q) {
@@ -1122,9 +1123,21 @@ static int box_build_units(EuBoxPlan* p, int bnd_lo, int bnd_hi, int grid_blocks
     return 0;
 }
 
+// number of boundary units the plan will have for these boundary planes (info[3], info[4]); -1 when the slab is too thin
+// for separate boundary and interior units
+int eu_box_plan_units(EuBoxPlan* p, int bnd_lo, int bnd_hi, bool, int info[6])
+{
+    if (bnd_lo + bnd_hi > p->z_hi - p->z_lo) return -1;
+    const int tiles = ((p->nx + p->tx - 1)/p->tx)*((p->ny + p->ty - 1)/p->ty);
+    eu_box_plan_info(p, info);
+    info[3] = bnd_lo > 0 ? tiles : 0;
+    info[4] = bnd_hi > 0 ? tiles : 0;
+    return 0;
+}
+
 template <bool ROCKS, bool MULTIROCK, bool CAP>
 static int launch_box(EuBoxPlan* p, const EuGridDev& g, const EuTablesDev& t, const EuFastDev& f, const EuStepArgs& a,
-                      const EuHaloDev& halo, int cur, int slice_lo, int bnd_lo, int bnd_hi, cudaStream_t st)
+                      const EuHaloDev& halo, int cur, int slice_lo, int slice_hi, int bnd_lo, int bnd_hi, cudaStream_t st)
 {
     const size_t tab_bytes = eu_fast_smem_bytes(t);
     static int stages_env = -1;
@@ -1170,24 +1183,24 @@ static int launch_box(EuBoxPlan* p, const EuGridDev& g, const EuTablesDev& t, co
         ++launches;
     }
     const int blocks = std::min(grid_full, p->n_units);
-    kern<<<blocks, p->threads, lay.total, st>>>(p->mapS[cur], p->mapPc[cur], p->mapQG, p->mapT, g, t, f, a, halo, lay.b, slice_lo, (int)tab_bytes);
+    kern<<<blocks, p->threads, lay.total, st>>>(p->mapS[cur], p->mapPc[cur], p->mapQG, p->mapT, g, t, f, a, halo, lay.b, slice_lo, slice_hi, (int)tab_bytes);
     return launches;
 }
 
 // one substep of the own planes [z_lo, z_hi) with the box kernel; returns the number of launches, -1 on error
 int eu_launch_box_step(EuBoxPlan* p, const EuGridDev& g, const EuTablesDev& t, const EuFastDev& f, const EuStepArgs& a,
-                       const EuHaloDev& halo, int cur, int slice_lo, int bnd_lo, int bnd_hi, cudaStream_t st)
+                       const EuHaloDev& halo, int cur, int slice_lo, int slice_hi, int bnd_lo, int bnd_hi, cudaStream_t st)
 {
     const bool cap = a.method_capillary != 0;
     if (t.n_rocks > 1) {
-        return cap ? launch_box<true, true, true>(p, g, t, f, a, halo, cur, slice_lo, bnd_lo, bnd_hi, st)
-                   : launch_box<true, true, false>(p, g, t, f, a, halo, cur, slice_lo, bnd_lo, bnd_hi, st);
+        return cap ? launch_box<true, true, true>(p, g, t, f, a, halo, cur, slice_lo, slice_hi, bnd_lo, bnd_hi, st)
+                   : launch_box<true, true, false>(p, g, t, f, a, halo, cur, slice_lo, slice_hi, bnd_lo, bnd_hi, st);
     } else if (t.n_rocks == 1) {
-        return cap ? launch_box<true, false, true>(p, g, t, f, a, halo, cur, slice_lo, bnd_lo, bnd_hi, st)
-                   : launch_box<true, false, false>(p, g, t, f, a, halo, cur, slice_lo, bnd_lo, bnd_hi, st);
+        return cap ? launch_box<true, false, true>(p, g, t, f, a, halo, cur, slice_lo, slice_hi, bnd_lo, bnd_hi, st)
+                   : launch_box<true, false, false>(p, g, t, f, a, halo, cur, slice_lo, slice_hi, bnd_lo, bnd_hi, st);
     }
-    return cap ? launch_box<false, false, true>(p, g, t, f, a, halo, cur, slice_lo, bnd_lo, bnd_hi, st)
-               : launch_box<false, false, false>(p, g, t, f, a, halo, cur, slice_lo, bnd_lo, bnd_hi, st);
+    return cap ? launch_box<false, false, true>(p, g, t, f, a, halo, cur, slice_lo, slice_hi, bnd_lo, bnd_hi, st)
+               : launch_box<false, false, false>(p, g, t, f, a, halo, cur, slice_lo, slice_hi, bnd_lo, bnd_hi, st);
 }
 
 bool eu_fast_uses_stored_lam() { return kStoredLam; }

@@ -235,8 +235,10 @@ EuBoxPlan* eu_box_plan_create(int nx, int ny, int nz, int z_lo, int z_hi, double
                               double2* qg, double* T, const unsigned short* cmask, const int* irr_cells, int n_irr, double* acc_irr, int n_sms);
 void eu_box_plan_destroy(EuBoxPlan* p);
 void eu_box_plan_info(const EuBoxPlan* p, int out[6]);      // tile x, tile y, units, boundary units A, B, threads per block
+// builds (or reuses) the work units for `bnd_lo` / `bnd_hi` boundary planes at the two ends of the own range; info as above
+int eu_box_plan_units(EuBoxPlan* p, int bnd_lo, int bnd_hi, bool capillary, int info[6]);
 int eu_launch_box_step(EuBoxPlan* p, const EuGridDev& g, const EuTablesDev& t, const EuFastDev& f, const EuStepArgs& a,
-                       const EuHaloDev& halo, int cur, int slice_lo, int bnd_lo, int bnd_hi, cudaStream_t st);
+                       const EuHaloDev& halo, int cur, int slice_lo, int slice_hi, int bnd_lo, int bnd_hi, cudaStream_t st);
 int eu_fast_warps_per_sm(bool capillary);   // resident warps per SM of the substep kernel variant in use
 bool eu_fast_uses_stored_lam();      // build-time choice of eu_fast.cu: per-cell mobility pairs kept in HBM
 

@@ -173,7 +173,7 @@ template <bool ROCKS, bool MULTIROCK, bool CAP, int NS, int MINB>
 __global__ void __launch_bounds__(256, MINB)
 k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUtensorMap mapPc,
            const __grid_constant__ CUtensorMap mapQG, const __grid_constant__ CUtensorMap mapT,
-           EuGridDev g, EuTablesDev t, EuFastDev f, EuStepArgs a, EuHaloDev halo, EuBoxDev b, int slice_lo, int tab_bytes)
+           EuGridDev g, EuTablesDev t, EuFastDev f, EuStepArgs a, EuHaloDev halo, EuBoxDev b, int slice_lo, int slice_hi, int tab_bytes)
 {
     TabLayout L;
     L.nn = t.n_nodes_total; L.nb = t.n_buckets; L.nbd = double(t.n_buckets);
@@ -365,8 +365,10 @@ k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUt
                     double pcn;
                     const double sat = finish_cell<ROCKS, MULTIROCK, CAP, false>(L, t, f, a, c, m.S0, m.rock0, own0, inv_pv, acc, pcn);
                     if (range >= 0) {
+                        // ghost slot of this cell in the neighbour rank (the table covers the slices of the range)
                         const int first = (range == 0 ? slice_lo : halo.b_lo)*EU_SLICE;
-                        const int d = halo.dst[range][c - first];
+                        const int last = (range == 0 ? halo.a_hi : slice_hi)*EU_SLICE;
+                        const int d = (c >= first && c < last) ? halo.dst[range][c - first] : -1;
                         if (d >= 0) {
                             halo.peer_S[range][d] = sat;
                             if (CAP && halo.peer_pc[range]) halo.peer_pc[range][d] = pcn;
