@@ -198,7 +198,7 @@ def cartesian_grid(nx, ny, nz, dx=1.0, dy=1.0, dz=1.0, unique_bids=True, periodi
 # ----------------------------------------------------------------------------------
 # Faulted corner-point style grid (vertical pillars, columns shifted in z at fault planes)
 # ----------------------------------------------------------------------------------
-def faulted_grid(nx, ny, nz, dx=10.0, dy=10.0, dz=1.0, faults_i=(), faults_j=(), unique_bids=False):
+def faulted_grid(nx, ny, nz, dx=10.0, dy=10.0, dz=1.0, faults_i=(), faults_j=(), unique_bids=False, k0=0, k1=None):
     """Vertical-pillar corner-point grid whose cell columns are shifted in z at fault planes.
 
     ``faults_i`` = [(i_plane, throw_in_layers), ...]: columns with i >= i_plane are shifted up by
@@ -206,15 +206,17 @@ def faulted_grid(nx, ny, nz, dx=10.0, dy=10.0, dz=1.0, faults_i=(), faults_j=(),
     lateral face on the fault plane into two half-faces with different neighbours (so cells get 7
     or 8 faces, and neighbours lie in other k-layers); the unmatched parts at the top and bottom
     of a column become boundary faces.  Cell index c = i + nx*(j + ny*k) as for CpGrid.
+    ``k0``, ``k1``: only the cells of the layers [k0, k1) (neighbour ids stay global): the slab a rank generates.
     """
-    N = nx*ny*nz
+    k1 = nz if k1 is None else k1
+    N = nx*ny*(k1 - k0)
     sx = np.zeros(nx)
     for ip, t in faults_i:
         sx[ip:] += t
     sy = np.zeros(ny)
     for jp, t in faults_j:
         sy[jp:] += t
-    c = np.arange(N, dtype=np.int64)
+    c = np.arange(N, dtype=np.int64) + k0*nx*ny
     i = c % nx
     j = (c // nx) % ny
     k = c // (nx*ny)
@@ -298,7 +300,7 @@ def faulted_grid(nx, ny, nz, dx=10.0, dy=10.0, dz=1.0, faults_i=(), faults_j=(),
         hf_bid[bnd] = side[bnd]
         n_bid = 7
     return dict(
-        N=N,
+        N=N, first_cell=k0*nx*ny,
         hf_offset=_i32(hf_offset),
         hf_nbr=_i32(hf_nbr),
         hf_bid=_i32(hf_bid),
@@ -580,6 +582,68 @@ def c4_slab(nx, ny, nz, k0, k1, seed=44, velocity=(1e-6, 5e-7, 2.5e-7), dirichle
         cell_volume=_f64(np.ones(n)), cell_centroid=_f64(cc), porosity=_f64(poro), permeability=_f64(perm),
         rock_id=_i32(np.zeros(n)), sat0=_f64(sat0), hf_flux=_f64(flux),
     )
+
+
+C5_FAULTS_I = ((0.25, 1.5), (0.5, 2.25), (0.75, 0.75))      # (fraction of nx, throw in layers), as in config_c3
+C5_FAULTS_J = ((0.5, 3.0),)
+C5_GHOST_DEPTH = 4                                           # layers a lateral neighbour can be away (max throw 3, split faces)
+
+
+def c5_rocks():
+    return [corey_table(24, 0.10, 0.10, 0.30), corey_table(20, 0.15, 0.05, 0.22), corey_table(28, 0.05, 0.20, 0.40)]
+
+
+def c5_slab(nx, ny, nz, k0, k1, seed=42, velocity=(1e-6, 0.0, 0.0), dirichlet_sat=1.0):
+    """Layers [k0, k1) of the weak-scaling configuration C5 (BASELINE configs[4]): the C3 generator -- faulted
+    corner-point grid, dx = dy = 10 m, dz = 1 m, lognormal K with kz = 0.1 kx, phi in [0.05, 0.30], three rock types in
+    layer bands, Dirichlet S = 1 boundaries, flux of a constant velocity projected on the true face normals -- at
+    nx x ny x nz with nz = 122 layers per GPU.  Properties are seeded per layer, so the grid does not depend on how it
+    is partitioned.  Returns a dict in eu_grid_chunk form (global ids) plus ``sat0`` and ``hf_flux``."""
+    fi = [(int(f*nx), t) for f, t in C5_FAULTS_I]
+    fj = [(int(f*ny), t) for f, t in C5_FAULTS_J]
+    g = faulted_grid(nx, ny, nz, 10.0, 10.0, 1.0, faults_i=fi, faults_j=fj, k0=k0, k1=k1)
+    npl = nx*ny
+    n = g["N"]
+    kx = np.empty(n)
+    poro = np.empty(n)
+    sat0 = np.empty(n)
+    rock = np.empty(n, dtype=np.int32)
+    for k in range(k0, k1):
+        sl = slice((k - k0)*npl, (k - k0 + 1)*npl)
+        u1 = plane_uniform(seed, k, npl)
+        u2 = plane_uniform(seed + 7, k, npl)
+        z = np.sqrt(-2.0*np.log(1.0 - u1))*np.cos(2.0*np.pi*u2)
+        kx[sl] = np.exp(np.log(100.0*MILLIDARCY) + z)
+        poro[sl] = 0.05 + 0.25*plane_uniform(seed + 1, k, npl)
+        sat0[sl] = 0.25 + 0.1*(plane_uniform(seed + 2, k, npl) - 0.5)
+        rock[sl] = min((3*k)//nz, 2)
+    perm = np.zeros((n, 9))
+    perm[:, 0] = kx
+    perm[:, 4] = kx
+    perm[:, 8] = 0.1*kx
+    nbr = g["hf_nbr"]
+    bnd_hf = np.nonzero(nbr < 0)[0]
+    nrm = g["hf_normal"]
+    flux = ((velocity[0]*nrm[:, 0] + velocity[1]*nrm[:, 1]) + velocity[2]*nrm[:, 2])*g["hf_area"]
+    return dict(
+        first_cell=int(g["first_cell"]), n_cells=n,
+        hf_count=_i32(np.diff(g["hf_offset"])), hf_neighbour=_i32(nbr),
+        hf_area=g["hf_area"], hf_normal=nrm, hf_centroid=g["hf_centroid"],
+        bnd_hf=_i32(bnd_hf), bnd_kind=_i32(np.full(bnd_hf.shape[0], 1)),
+        bnd_sat=_f64(np.full(bnd_hf.shape[0], dirichlet_sat)),
+        bnd_partner_cell=_i32(np.full(bnd_hf.shape[0], -1)), bnd_partner_face=_i32(np.full(bnd_hf.shape[0], -1)),
+        cell_volume=g["cell_volume"], cell_centroid=g["cell_centroid"], porosity=_f64(poro), permeability=_f64(perm),
+        rock_id=rock, sat0=_f64(sat0), hf_flux=_f64(flux),
+    )
+
+
+def c5_fluid_case():
+    """The fluid / rock / solver-parameter part of C5 as a tiny Case (no grid arrays): three rock tables, V+G+C."""
+    g = cartesian_grid(1, 1, 1, unique_bids=False)
+    perm = np.zeros((1, 9))
+    perm[0, [0, 4, 8]] = 100.0*MILLIDARCY
+    return make_case("C5-fluid", g, poro=np.full(1, 0.2), perm=perm, rock_id=np.zeros(1, dtype=np.int32),
+                     rocks=c5_rocks(), sat0=np.zeros(1), gravity=[0.0, 0.0, -9.80665], hf_flux=np.zeros(6))
 
 
 def c4_fluid_case(capillary=False):
