@@ -364,7 +364,7 @@ __device__ __noinline__ double gather_cell_loop(const TabLayout& L, const EuGrid
 template <bool ROCKS, bool MULTIROCK, bool CAP, bool TENSOR>
 __device__ __forceinline__ double finish_cell(const TabLayout& L, const EuTablesDev& t, const EuFastDev& f, const EuStepArgs& a,
                                               int c, double S0, int rock0, const OwnMob<TENSOR>& own0, double inv_pv, double acc,
-                                              double& pcn)
+                                              double& pcn, bool pcs_given = false, double pcs = 1.0)
 {
     if (a.n_src > 0) {
         double rate = 0.0;
@@ -408,7 +408,7 @@ __device__ __forceinline__ double finish_cell(const TabLayout& L, const EuTables
     }
     if (!kStoredLam) {           // no pair arrays: only the capillary pressure of the new state
         if (CAP) {
-            pcn = Mob<ROCKS, MULTIROCK>::pc(L, rock0, sat, ROCKS ? f.pcscale[c] : 1.0);
+            pcn = Mob<ROCKS, MULTIROCK>::pc(L, rock0, sat, ROCKS ? (pcs_given ? pcs : f.pcscale[c]) : 1.0);
             a.pc_out[c] = pcn;
         }
         return sat;
@@ -983,7 +983,7 @@ BoxLayout box_layout(const EuBoxPlan& p, bool cap, bool multirock, int stages, s
     b.nx = p.nx; b.ny = p.ny; b.nz = p.nz; b.tx = p.tx; b.ty = p.ty;
     b.stages = stages;
     const int cells = (p.tx + 2)*(p.ty + 2);
-    b.lam_bytes = r128(cells*(cap ? 32 : 16));
+    b.lam_bytes = cap ? 2*r128(cells*16) : r128(cells*16);      // {lw, lo} entries, then (capillary) {S, pc} entries
     b.rk_bytes = (cap && multirock) ? r128(cells) : 0;
     b.qg_bytes = r128((p.tx + 1)*(p.ty + 1)*16);
     b.T_bytes = cap ? r128((p.tx + 2)*(p.ty + 1)*8) : 0;

@@ -192,7 +192,8 @@ k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUt
         const unsigned long long key = *a.fail_key;
         if (key != ~0ULL && (unsigned)(key >> 32) < (unsigned)a.substep) return;
     }
-    constexpr int E = CAP ? 32 : 16;                            // bytes per ring entry: {lw, lo} [S, pc]
+    constexpr int E = 16;                                       // bytes per ring entry: {lw, lo}; with the capillary term a second
+    const int oB = b.lam_bytes/2;                               // array {S, pc} follows at oB (two 16-byte arrays: conflict-free LDS.128)
     const int tx = b.tx, ty = b.ty, txp = tx + 2, txf = tx + 1, txs = tx + 4;      // row lengths: ring / T boxes, face boxes, S boxes
     const int lx = tid % tx, ly = tid/tx;
     const bool in_tile = tid < tx*ty;
@@ -273,24 +274,34 @@ k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUt
             if (qx >= 0 && qx < b.nx && qy >= 0 && qy < b.ny) hc = qx + b.nx*qy + (z0 - 1)*D;
         }
         unsigned mk = 0u;                                       // mask of the faces outside the axis planes, plane k (none for z0-1)
+        int rock_n = 0, rock_hn = 0;                            // rock ids of plane k+1: own cell, halo cell
+        if (MULTIROCK && z0 < b.nz) {
+            if (active) rock_n = __ldg(f.rock8 + c + D);
+            if (hc >= 0) rock_hn = __ldg(f.rock8 + hc + D);
+        }
         // ring buffers: next (plane k+1, written in phase A), cur (plane k, read in phase B), and the one in between
         int r_next = ((z0 % 3) + 3) % 3, r_cur = (r_next + 2) % 3;
         for (int k = z0 - 1; k < z1; ++k) {
             // operands of plane k that are not staged: requested now, used after the barrier
             double inv_pv = 0.0;
             const bool update = active && k >= z0;
-            if (update) inv_pv = ldg_f64(f.inv_porevol + c);
+            double pcs = 1.0;
+            if (update) {
+                inv_pv = ldg_f64(f.inv_porevol + c);
+                if (CAP && ROCKS) pcs = ldg_f64(f.pcscale + c);
+            }
             // faces outside the axis planes were summed per cell by k_box_irregular before this launch; the mask of a
             // plane is fetched one step ahead so that the load of the sum need not wait for it
             const unsigned mask = mk;
             double acc_irr = 0.0;
             if (mask) acc_irr = ldg_f64(b.acc_irr + c);
             mk = (active && k + 1 < z1) ? unsigned(__ldg(b.cmask + c + D)) : 0u;
-            const bool up_ok = k + 1 < b.nz;
-            int rock1 = 0, rock_h = 0;
+            // rock ids of plane k+1 were requested a step ago; those of plane k+2 are requested now
+            const int rock1 = rock_n, rock_h = rock_hn;
             if (MULTIROCK) {
-                if (active && up_ok) rock1 = __ldg(f.rock8 + c + D);
-                if (hc >= 0 && up_ok) rock_h = __ldg(f.rock8 + hc + D);
+                const bool up2 = k + 2 < b.nz;
+                rock_n = (active && up2) ? int(__ldg(f.rock8 + c + 2*D)) : 0;
+                rock_hn = (hc >= 0 && up2) ? int(__ldg(f.rock8 + hc + 2*D)) : 0;
             }
             const unsigned char* st = stage0 + slot*b.stage_bytes;
             mbar_wait(base_u32 + b.off_bar + 8*slot, par);
@@ -301,23 +312,21 @@ k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUt
                 S1 = *reinterpret_cast<const double*>(st + b.off_S + o_S);
                 if (CAP) pc1 = *reinterpret_cast<const double*>(st + b.off_pc + o_S);
                 Mob<ROCKS, MULTIROCK>::both(L, t, rock1, S1, lw1, lo1);
+                *reinterpret_cast<double2*>(ring_next + o_ring) = make_double2(lw1, lo1);
                 if (CAP) {
-                    *reinterpret_cast<double4*>(ring_next + o_ring) = make_double4(lw1, lo1, S1, pc1);
+                    *reinterpret_cast<double2*>(ring_next + oB + o_ring) = make_double2(S1, pc1);
                     if (MULTIROCK) rk0[r_next*b.rk_bytes + o_rk] = (unsigned char)rock1;
-                } else {
-                    *reinterpret_cast<double2*>(ring_next + o_ring) = make_double2(lw1, lo1);
                 }
             }
             if (has_halo) {
                 const double Sh = *reinterpret_cast<const double*>(st + b.off_S + o_S_h);
                 double lwh, loh;
                 Mob<ROCKS, MULTIROCK>::both(L, t, rock_h, Sh, lwh, loh);
+                *reinterpret_cast<double2*>(ring_next + o_ring_h) = make_double2(lwh, loh);
                 if (CAP) {
                     const double ph = *reinterpret_cast<const double*>(st + b.off_pc + o_S_h);
-                    *reinterpret_cast<double4*>(ring_next + o_ring_h) = make_double4(lwh, loh, Sh, ph);
+                    *reinterpret_cast<double2*>(ring_next + oB + o_ring_h) = make_double2(Sh, ph);
                     if (MULTIROCK) rk0[r_next*b.rk_bytes + o_rk_h] = (unsigned char)rock_h;
-                } else {
-                    *reinterpret_cast<double2*>(ring_next + o_ring_h) = make_double2(lwh, loh);
                 }
             }
             __syncthreads();
@@ -344,14 +353,13 @@ k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUt
                     int rx[4];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
+                        const double2 e = *reinterpret_cast<const double2*>(ring + dr[q]);
+                        lwn[q] = e.x; lon[q] = e.y; Sx[q] = 0.0; Px[q] = 0.0; Tx[q] = 0.0; rx[q] = 0;
                         if (CAP) {
-                            const double4 e = *reinterpret_cast<const double4*>(ring + dr[q]);
-                            lwn[q] = e.x; lon[q] = e.y; Sx[q] = e.z; Px[q] = e.w;
+                            const double2 e2 = *reinterpret_cast<const double2*>(ring + oB + dr[q]);
+                            Sx[q] = e2.x; Px[q] = e2.y;
                             rx[q] = MULTIROCK ? int(rk[dk[q]]) : 0;
                             Tx[q] = *reinterpret_cast<const double*>(TT + dt[q]);
-                        } else {
-                            const double2 e = *reinterpret_cast<const double2*>(ring + dr[q]);
-                            lwn[q] = e.x; lon[q] = e.y; Sx[q] = 0.0; Px[q] = 0.0; Tx[q] = 0.0; rx[q] = 0;
                         }
                         qg[q] = *reinterpret_cast<const double2*>(QG + dq[q]);
                     }
@@ -363,7 +371,7 @@ k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUt
                     OwnMob<false> own0;
                     own0.lw[0] = m.lw0; own0.lo[0] = m.lo0;
                     double pcn;
-                    const double sat = finish_cell<ROCKS, MULTIROCK, CAP, false>(L, t, f, a, c, m.S0, m.rock0, own0, inv_pv, acc, pcn);
+                    const double sat = finish_cell<ROCKS, MULTIROCK, CAP, false>(L, t, f, a, c, m.S0, m.rock0, own0, inv_pv, acc, pcn, true, pcs);
                     if (range >= 0) {
                         // ghost slot of this cell in the neighbour rank (the table covers the slices of the range)
                         const int first = (range == 0 ? slice_lo : halo.b_lo)*EU_SLICE;
