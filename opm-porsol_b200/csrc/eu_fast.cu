@@ -931,7 +931,7 @@ struct EuBoxPlan {
     int tx = 0, ty = 0, threads = 0;
     CUtensorMap mapS[2], mapPc[2], mapQG, mapT;
     int4* d_units = nullptr;
-    int n_units = 0, n_bnd_units[2] = { 0, 0 };
+    int n_units = 0, n_bnd_units[2] = { 0, 0 }, n_flagged = 0;
     int units_key[5] = { -1, -1, -1, -1, -1 };      // (bnd planes lo, hi, grid blocks, lz override, cap) the unit list was built for
     const unsigned short* cmask = nullptr;
     const int* irr_cells = nullptr;
@@ -1072,9 +1072,29 @@ void eu_box_plan_info(const EuBoxPlan* p, int out[6])
     out[0] = p->tx; out[1] = p->ty; out[2] = p->n_units; out[3] = p->n_bnd_units[0]; out[4] = p->n_bnd_units[1]; out[5] = p->threads;
 }
 
-// Work units: tiles x z-chunks.  The planes next to a slab boundary (bnd_lo / bnd_hi planes at the two ends of the own
-// range; 0 without a neighbour rank) form short chunks that come first in the list: their results are pushed to the
-// neighbour rank.  The chunk length of the rest balances (units per block) x (planes + 1 prologue step per unit).
+// Work units: tiles x z-chunks of the own planes.  With a neighbour rank below / above, the chunks that contain the
+// bnd_lo / bnd_hi planes whose cells the neighbour keeps as ghosts are flagged (bit 0 / bit 1) and come first in the list:
+// the kernel pushes those cells' results to the neighbour as it sweeps them and counts the finished flagged units; the
+// neighbour needs the flag only when its next substep starts, a whole kernel later.  The chunk length balances
+// (units per block) x (planes + 1 prologue step per unit).
+static int box_chunks(const EuBoxPlan* p, int grid_blocks, int lz_env, int min_len)
+{
+    const int tiles = ((p->nx + p->tx - 1)/p->tx)*((p->ny + p->ty - 1)/p->ty);
+    const int planes = p->z_hi - p->z_lo;
+    int best_chunks = 1;
+    double best = 1e300;
+    for (int chunks = 1; chunks <= planes; ++chunks) {
+        const double len = double(planes)/chunks;
+        if (len < std::max(min_len, 1) && chunks > 1) break;
+        if (lz_env > 0) { if (len <= lz_env || chunks == planes) { best_chunks = chunks; break; } continue; }
+        if (len > 64.0) continue;
+        const double rounds = double(((long long)chunks*tiles + grid_blocks - 1)/grid_blocks);
+        const double cost = rounds*(len + 1.3);
+        if (cost < best - 1e-9) { best = cost; best_chunks = chunks; }
+    }
+    return best_chunks;
+}
+
 static int box_build_units(EuBoxPlan* p, int bnd_lo, int bnd_hi, int grid_blocks, bool cap)
 {
     const char* e = getenv("EU_BOX_LZ");
@@ -1082,38 +1102,28 @@ static int box_build_units(EuBoxPlan* p, int bnd_lo, int bnd_hi, int grid_blocks
     if (p->units_key[0] == bnd_lo && p->units_key[1] == bnd_hi && p->units_key[2] == grid_blocks && p->units_key[3] == lz_env &&
         p->units_key[4] == int(cap) && p->d_units) return 0;
     const int tiles_x = (p->nx + p->tx - 1)/p->tx, tiles_y = (p->ny + p->ty - 1)/p->ty;
-    const int tiles = tiles_x*tiles_y;
-    const int zi0 = p->z_lo + bnd_lo, zi1 = p->z_hi - bnd_hi;          // interior planes
-    int lz = 32;
-    if (lz_env > 0) lz = lz_env;
-    else if (zi1 > zi0) {
-        double best = 1e300;
-        for (int L = 4; L <= 64; ++L) {
-            const long long chunks = (zi1 - zi0 + L - 1)/L;
-            const long long units = chunks*tiles;
-            const double rounds = double((units + grid_blocks - 1)/grid_blocks);
-            const double len = double(zi1 - zi0)/double(chunks);
-            const double cost = rounds*(len + 1.3);
-            if (cost < best - 1e-9) { best = cost; lz = L; }
-        }
-    }
+    const int planes = p->z_hi - p->z_lo;
+    const int chunks = box_chunks(p, grid_blocks, lz_env, std::max(bnd_lo, bnd_hi));
     std::vector<int4> units;
-    auto add = [&](int z0, int z1, int flags) {
+    auto add = [&](int q) {
+        const int z0 = p->z_lo + int((long long)planes*q/chunks), z1 = p->z_lo + int((long long)planes*(q + 1)/chunks);
+        const int flags = ((bnd_lo > 0 && q == 0) ? 1 : 0) | ((bnd_hi > 0 && q == chunks - 1) ? 2 : 0);
+        if (z1 <= z0) return;
         for (int tyi = 0; tyi < tiles_y; ++tyi)
             for (int txi = 0; txi < tiles_x; ++txi)
                 units.push_back(make_int4((txi*p->tx) | ((tyi*p->ty) << 16), z0, z1, flags));
     };
-    // (the caller guarantees bnd_lo + bnd_hi <= own planes: eu_box_plan_units)
-    p->n_bnd_units[0] = p->n_bnd_units[1] = 0;
-    if (bnd_lo > 0) { add(p->z_lo, zi0, 1); p->n_bnd_units[0] = tiles; }
-    if (bnd_hi > 0) { add(zi1, p->z_hi, 2); p->n_bnd_units[1] = tiles; }
-    if (zi1 > zi0) {
-        const int chunks = (zi1 - zi0 + lz - 1)/lz;
-        for (int q = 0; q < chunks; ++q) {
-            const int a0 = zi0 + int((long long)(zi1 - zi0)*q/chunks), a1 = zi0 + int((long long)(zi1 - zi0)*(q + 1)/chunks);
-            if (a1 > a0) add(a0, a1, 0);
-        }
+    // flagged chunks first
+    if (bnd_lo > 0) add(0);
+    if (bnd_hi > 0 && (chunks > 1 || bnd_lo == 0)) add(chunks - 1);
+    for (int q = 0; q < chunks; ++q) {
+        if ((bnd_lo > 0 && q == 0) || (bnd_hi > 0 && q == chunks - 1)) continue;
+        add(q);
     }
+    p->n_bnd_units[0] = bnd_lo > 0 ? tiles_x*tiles_y : 0;
+    p->n_bnd_units[1] = bnd_hi > 0 ? tiles_x*tiles_y : 0;
+    p->n_flagged = 0;
+    for (const int4& un : units) if (un.w) ++p->n_flagged;
     if (p->d_units) { cudaFree(p->d_units); p->d_units = nullptr; }
     p->n_units = int(units.size());
     if (units.empty()) return 0;
@@ -1123,11 +1133,11 @@ static int box_build_units(EuBoxPlan* p, int bnd_lo, int bnd_hi, int grid_blocks
     return 0;
 }
 
-// number of boundary units the plan will have for these boundary planes (info[3], info[4]); -1 when the slab is too thin
-// for separate boundary and interior units
+// number of flagged units the plan will have for these boundary planes (info[3], info[4]); -1 when the slab is thinner than
+// the boundary ranges
 int eu_box_plan_units(EuBoxPlan* p, int bnd_lo, int bnd_hi, bool, int info[6])
 {
-    if (bnd_lo + bnd_hi > p->z_hi - p->z_lo) return -1;
+    if (std::max(bnd_lo, bnd_hi) > p->z_hi - p->z_lo) return -1;
     const int tiles = ((p->nx + p->tx - 1)/p->tx)*((p->ny + p->ty - 1)/p->ty);
     eu_box_plan_info(p, info);
     info[3] = bnd_lo > 0 ? tiles : 0;
@@ -1174,6 +1184,7 @@ static int launch_box(EuBoxPlan* p, const EuGridDev& g, const EuTablesDev& t, co
     lay.b.units = p->d_units;
     lay.b.n_units = p->n_units;
     lay.b.cmask = p->cmask;
+    lay.b.n_flagged = p->n_flagged;
     lay.b.acc_irr = p->acc_irr;
     int launches = 1;
     if (p->n_irr > 0) {

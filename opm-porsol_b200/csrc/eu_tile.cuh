@@ -32,12 +32,13 @@ struct EuBoxDev {
     int nx, ny, nz;               // local box
     int tx, ty;                   // tile
     int n_units;
-    const int4* units;            // {x0 | y0 << 16, z0, z1 (exclusive), flags: bit 0/1 = halo range A/B, i.e. push results to a peer}
+    const int4* units;            // {x0 | y0 << 16, z0, z1 (exclusive), flags: bit 0 / 1 = holds cells of halo range A / B (pushed to a peer)}
     int stages;                   // bundles in flight
     int off_bar, off_lam, off_rk, off_stage;      // byte offsets in dynamic shared memory (from the 128-aligned base)
     int lam_bytes, rk_bytes, stage_bytes;
     int off_S, off_pc, off_qg, off_T;             // inside a stage
     int qg_bytes, T_bytes;                        // one axis' box
+    int n_flagged;                // units with a push flag (they are the first of the list)
     const unsigned short* cmask;  // per cell: record slots with faces outside the axis planes
     const double* acc_irr;        // per cell with a non-zero mask: sum of those faces' contributions (k_box_irregular)
 };
@@ -218,43 +219,70 @@ k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUt
     unsigned char* const rk0 = base + b.off_rk;
     int slot = 0;                                               // stage of the current bundle; par = phase parity of its mbarrier
     unsigned par = 0;
+    if (halo.enabled && int(blockIdx.x) < b.n_flagged && tid < halo.n_wait) {
+        // this block sweeps planes next to a slab boundary: the ghosts of the previous substep must have landed before
+        // any TMA load reads them (flagged units are the first of the list, so every block that has one gets here)
+        const volatile unsigned* fl = halo.my_flags + halo.wait_rank[tid];
+        const long long t0 = clock64();
+        while ((int)(*fl - (halo.epoch - 1u)) < 0) {
+            __nanosleep(100);
+            if (clock64() - t0 > halo.timeout_cycles) { atomicExch(halo.err_flag, 1); break; }
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    // ---- producer (thread 0): one bundle per plane, NS - 1 planes ahead of the sweep, ACROSS work units -- the first
+    // bundles of the next unit are already in flight while the last planes of the current one are swept
+    // (its state lives in shared memory, behind the mbarriers: no registers of the sweep are spent on it)
+    struct Producer { int4 unit, next; int pu, pk, slot, pad; };
+    Producer* const P = reinterpret_cast<Producer*>(base + b.off_bar + 64);
+    auto produce = [&]() {
+        int pu = P->pu;
+        if (pu >= b.n_units) return;
+        const int4 un = P->unit;
+        const int x0 = un.x & 0xffff, y0 = un.x >> 16, k = P->pk, ps = P->slot;
+        const unsigned bar = base_u32 + b.off_bar + 8*ps;
+        const unsigned st = base_u32 + b.off_stage + unsigned(ps)*unsigned(b.stage_bytes);
+        mbar_expect_tx(bar, bundle_bytes);
+        tma_load_3d(st + b.off_S, &mapS, x0 - 2, y0 - 1, k + 1, bar);
+        if (CAP) tma_load_3d(st + b.off_pc, &mapPc, x0 - 2, y0 - 1, k + 1, bar);
+        tma_load_4d(st + b.off_qg, &mapQG, 2*(x0 - 1), y0, k, 0, bar);
+        tma_load_4d(st + b.off_qg + b.qg_bytes, &mapQG, 2*x0, y0 - 1, k, 1, bar);
+        tma_load_4d(st + b.off_qg + 2*b.qg_bytes, &mapQG, 2*x0, y0, k, 2, bar);
+        if (CAP) {
+            tma_load_4d(st + b.off_T, &mapT, x0 - 2, y0, k, 0, bar);
+            tma_load_4d(st + b.off_T + b.T_bytes, &mapT, x0, y0 - 1, k, 1, bar);
+            tma_load_4d(st + b.off_T + 2*b.T_bytes, &mapT, x0, y0, k, 2, bar);
+        }
+        P->slot = (ps + 1 == NS) ? 0 : ps + 1;
+        if (k + 1 >= un.z) {                                    // on to the block's next unit
+            pu += gridDim.x;
+            P->pu = pu;
+            const int4 nx = P->next;
+            P->unit = nx;
+            P->pk = nx.y - 1;
+            if (pu + int(gridDim.x) < b.n_units) P->next = __ldg(b.units + pu + gridDim.x);
+        } else {
+            P->pk = k + 1;
+        }
+    };
+    if (tid == 0) {
+        const int pu = blockIdx.x;
+        P->pu = pu; P->slot = 0;
+        int4 un = make_int4(0, 0, 0, 0);
+        if (pu < b.n_units) un = __ldg(b.units + pu);
+        P->unit = un;
+        P->pk = un.y - 1;
+        if (pu + int(gridDim.x) < b.n_units) P->next = __ldg(b.units + pu + gridDim.x);
+        for (int j = 0; j < NS; ++j) produce();
+    }
+    bool first_step = true;                                     // nothing to refill at the block's very first step
 
     for (int u = blockIdx.x; u < b.n_units; u += gridDim.x) {
         const int4 unit = __ldg(b.units + u);
         const int x0 = unit.x & 0xffff, y0 = unit.x >> 16, z0 = unit.y, z1 = unit.z;
-        const int nb = z1 - z0 + 1;                             // bundles = steps k = z0-1 .. z1-1
-        const int range = (unit.w & 1) ? 0 : ((unit.w & 2) ? 1 : -1);
-        if (range >= 0 && tid < halo.n_wait) {
-            // ghosts of the previous substep must have landed before this unit's TMA loads read them
-            const volatile unsigned* fl = halo.my_flags + halo.wait_rank[tid];
-            const long long t0 = clock64();
-            while ((int)(*fl - (halo.epoch - 1u)) < 0) {
-                __nanosleep(100);
-                if (clock64() - t0 > halo.timeout_cycles) { atomicExch(halo.err_flag, 1); break; }
-            }
-            __threadfence_system();
-        }
-        __syncthreads();                                        // every stage and ring buffer of the previous unit is free
-        // bundle of plane k into stage s
-        auto issue = [&](int k, int s) {
-            const unsigned bar = base_u32 + b.off_bar + 8*s;
-            const unsigned st = base_u32 + b.off_stage + unsigned(s)*unsigned(b.stage_bytes);
-            mbar_expect_tx(bar, bundle_bytes);
-            tma_load_3d(st + b.off_S, &mapS, x0 - 2, y0 - 1, k + 1, bar);
-            if (CAP) tma_load_3d(st + b.off_pc, &mapPc, x0 - 2, y0 - 1, k + 1, bar);
-            tma_load_4d(st + b.off_qg, &mapQG, 2*(x0 - 1), y0, k, 0, bar);
-            tma_load_4d(st + b.off_qg + b.qg_bytes, &mapQG, 2*x0, y0 - 1, k, 1, bar);
-            tma_load_4d(st + b.off_qg + 2*b.qg_bytes, &mapQG, 2*x0, y0, k, 2, bar);
-            if (CAP) {
-                tma_load_4d(st + b.off_T, &mapT, x0 - 2, y0, k, 0, bar);
-                tma_load_4d(st + b.off_T + b.T_bytes, &mapT, x0, y0 - 1, k, 1, bar);
-                tma_load_4d(st + b.off_T + 2*b.T_bytes, &mapT, x0, y0, k, 2, bar);
-            }
-        };
-        if (tid == 0) {
-            int s = slot;
-            for (int j = 0; j < NS && j < nb; ++j) { issue(z0 - 1 + j, s); s = (s + 1 == NS) ? 0 : s + 1; }
-        }
+        const int push = unit.w & 3;
+        __syncthreads();                                        // the ring buffers of the previous unit are free
         // ---- own column: the cell of plane z0-1 (operands of the first carried face)
         const int gx = x0 + lx, gy = y0 + ly;
         const bool active = in_tile && gx < b.nx && gy < b.ny;
@@ -330,8 +358,9 @@ k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUt
                 }
             }
             __syncthreads();
-            // the stage of the previous step is free now: refill it with the bundle NS - 1 planes ahead
-            if (tid == 0 && k >= z0 && k - 1 + NS < z1) issue(k - 1 + NS, slot == 0 ? NS - 1 : slot - 1);
+            // the stage of the previous step is free now: refill it with the next bundle of the stream
+            if (tid == 0 && !first_step) produce();
+            first_step = false;
             // ---- phase B: faces of plane k
             if (in_tile) {
                 const unsigned char* QG = st + b.off_qg + o_F;
@@ -372,14 +401,18 @@ k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUt
                     own0.lw[0] = m.lw0; own0.lo[0] = m.lo0;
                     double pcn;
                     const double sat = finish_cell<ROCKS, MULTIROCK, CAP, false>(L, t, f, a, c, m.S0, m.rock0, own0, inv_pv, acc, pcn, true, pcs);
-                    if (range >= 0) {
-                        // ghost slot of this cell in the neighbour rank (the table covers the slices of the range)
-                        const int first = (range == 0 ? slice_lo : halo.b_lo)*EU_SLICE;
-                        const int last = (range == 0 ? halo.a_hi : slice_hi)*EU_SLICE;
-                        const int d = (c >= first && c < last) ? halo.dst[range][c - first] : -1;
-                        if (d >= 0) {
-                            halo.peer_S[range][d] = sat;
-                            if (CAP && halo.peer_pc[range]) halo.peer_pc[range][d] = pcn;
+                    if (push) {
+                        // ghost slot of this cell in a neighbour rank (the tables cover the slices of the two ranges)
+#pragma unroll
+                        for (int r = 0; r < 2; ++r) {
+                            if (!((push >> r) & 1)) continue;
+                            const int first = (r == 0 ? slice_lo : halo.b_lo)*EU_SLICE;
+                            const int last = (r == 0 ? halo.a_hi : slice_hi)*EU_SLICE;
+                            const int d = (c >= first && c < last) ? halo.dst[r][c - first] : -1;
+                            if (d >= 0) {
+                                halo.peer_S[r][d] = sat;
+                                if (CAP && halo.peer_pc[r]) halo.peer_pc[r][d] = pcn;
+                            }
                         }
                     }
                 }
@@ -393,17 +426,21 @@ k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUt
             r_cur = r_next;
             r_next = (r_next == 2) ? 0 : r_next + 1;
         }
-        if (range >= 0) {
-            // all pushes of this unit, one system-scope fence, then the finished-unit counter of the range
-            __threadfence_system();
+        if (push) {
+            // all pushes of this unit are ordered before thread 0 by the block barrier; its system-scope fence is cumulative
+            // (one fence per unit instead of one per thread), then the finished-unit counters of the unit's ranges
             __syncthreads();
             if (tid == 0) {
-                const unsigned before = atomicAdd(halo.counter[range], 1u);
-                if (before + 1u == halo.total[range]) {
-                    *halo.counter[range] = 0u;
-                    __threadfence_system();
-                    *(volatile unsigned*)halo.peer_flag[range] = halo.epoch;
-                    __threadfence_system();
+                __threadfence_system();
+                for (int r = 0; r < 2; ++r) {
+                    if (!((push >> r) & 1)) continue;
+                    const unsigned before = atomicAdd(halo.counter[r], 1u);
+                    if (before + 1u == halo.total[r]) {
+                        *halo.counter[r] = 0u;
+                        __threadfence_system();
+                        *(volatile unsigned*)halo.peer_flag[r] = halo.epoch;
+                        __threadfence_system();
+                    }
                 }
             }
         }
