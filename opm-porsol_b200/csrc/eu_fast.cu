@@ -1032,10 +1032,12 @@ EuBoxPlan* eu_box_plan_create(int nx, int ny, int nz, int z_lo, int z_hi, double
                 for (int ty = 1; ty <= 32 && tx*ty <= 256 && ty <= ny; ++ty) {
                     const double halo = double((tx + 2)*(ty + 2))/double(tx*ty);
                     const double idle_x = double(((nx + tx - 1)/tx)*tx)/nx, idle_y = double(((ny + ty - 1)/ty)*ty)/ny;
-                    const double warps = double((tx*ty + 31)/32*32)/double(tx*ty);
-                    // curve evaluations are about a fifth of a cell's work; idle lanes cost everything; a tile row that
-                    // is a multiple of 32 cells keeps the warps' shared-memory rows conflict-free
-                    double cost = (0.8 + 0.2*halo)*idle_x*idle_y*warps*(tx*ty < 128 ? 1.3 : 1.0)*((tx % 32) ? 1.03 : 1.0);
+                    const double fill = double(tx*ty)/double((tx*ty + 31)/32*32);
+                    // fitted to tile sweeps on B200 (C2 at 100^3 / 200^3, C4 at 512^2 x 256; profiles/README.md): the halo
+                    // cells cost about a third of an own cell, short rows lose a little (row segments of the TMA boxes
+                    // and of the ring reads), idle lanes cost everything
+                    const int thr = (tx*ty + 31)/32*32;
+                    const double cost = (1.0 + 0.35*(halo - 1.0))*(1.0 + 1.5/tx)*idle_x*idle_y/fill*(1.0 + 0.5*(256 - thr)/256.0);   // (small blocks: fewer warps per SM)
                     if (cost < best - 1e-12) { best = cost; p->tx = tx; p->ty = ty; }
                 }
             }
