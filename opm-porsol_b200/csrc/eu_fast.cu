@@ -975,7 +975,7 @@ inline int r128(int v) { return (v + 127) & ~127; }
 
 // shared-memory layout of the box kernel for a tile shape
 struct BoxLayout { EuBoxDev b; size_t total; };
-BoxLayout box_layout(const EuBoxPlan& p, bool cap, bool multirock, int stages, size_t tab_bytes)
+BoxLayout box_layout(const EuBoxPlan& p, bool cap, bool multirock, int stages, size_t tab_bytes, bool share = false)
 {
     BoxLayout o;
     std::memset(&o, 0, sizeof(o));
@@ -996,7 +996,11 @@ BoxLayout box_layout(const EuBoxPlan& p, bool cap, bool multirock, int stages, s
     b.off_bar = 0;
     b.off_lam = 128;
     b.off_rk = b.off_lam + 3*b.lam_bytes;
-    b.off_stage = b.off_rk + 3*b.rk_bytes;
+    b.fx_bytes = share ? r128(p.ty*(p.tx + 1)*8) : 0;
+    b.fy_bytes = share ? r128((p.ty + 1)*p.tx*8) : 0;
+    b.off_fx = b.off_rk + 3*b.rk_bytes;
+    b.off_fy = b.off_fx + 2*b.fx_bytes;
+    b.off_stage = b.off_fy + 2*b.fy_bytes;
     o.total = tab_bytes + 128 /* alignment slack */ + size_t(b.off_stage) + size_t(stages)*size_t(b.stage_bytes);
     return o;
 }
@@ -1159,20 +1163,25 @@ static int launch_box(EuBoxPlan* p, const EuGridDev& g, const EuTablesDev& t, co
     if (minb_pre < 0) { const char* e = getenv("EU_BOX_MINB"); minb_pre = e ? atoi(e) : 0; }
     const int want_blocks = minb_pre ? minb_pre : (CAP ? 2 : 3);
     int stages = stages_env ? stages_env : 3;
-    BoxLayout lay = box_layout(*p, CAP, MULTIROCK, stages, tab_bytes);
+    // EU_BOX_SHARE (tuning knob): lateral faces evaluated once per tile and exchanged through shared memory; default: with
+    // the capillary term
+    static int share_env = -1;
+    if (share_env < 0) { const char* e = getenv("EU_BOX_SHARE"); share_env = e ? (atoi(e) != 0 ? 1 : 0) : 2; }
+    const bool share = CAP && (share_env == 2 ? true : share_env == 1);
+    BoxLayout lay = box_layout(*p, CAP, MULTIROCK, stages, tab_bytes, share);
     const size_t budget = size_t(227*1024)/want_blocks - 1024;
-    while (!stages_env && stages > 2 && lay.total > budget) lay = box_layout(*p, CAP, MULTIROCK, --stages, tab_bytes);
+    while (!stages_env && stages > 2 && lay.total > budget) lay = box_layout(*p, CAP, MULTIROCK, --stages, tab_bytes, share);
     // EU_BOX_MINB (tuning knob): resident blocks per SM the kernel is compiled for (register budget 2: 128, 3: 80)
     static int minb_env = -1;
     if (minb_env < 0) { const char* e = getenv("EU_BOX_MINB"); minb_env = e ? atoi(e) : 0; }
     const bool two = minb_env ? minb_env == 2 : CAP;
-    auto kern3 = stages == 2 ? k_box_step<ROCKS, MULTIROCK, CAP, 2, 3> : (stages == 3 ? k_box_step<ROCKS, MULTIROCK, CAP, 3, 3> : k_box_step<ROCKS, MULTIROCK, CAP, 4, 3>);
-    auto kern2 = stages == 2 ? k_box_step<ROCKS, MULTIROCK, CAP, 2, 2> : (stages == 3 ? k_box_step<ROCKS, MULTIROCK, CAP, 3, 2> : k_box_step<ROCKS, MULTIROCK, CAP, 4, 2>);
-    auto kern4 = stages == 2 ? k_box_step<ROCKS, MULTIROCK, CAP, 2, 4> : k_box_step<ROCKS, MULTIROCK, CAP, 3, 4>;
-    auto kern = minb_env == 4 ? kern4 : (two ? kern2 : kern3);
+    auto kern3 = stages == 2 ? k_box_step<ROCKS, MULTIROCK, CAP, 2, 3, false> : (stages == 3 ? k_box_step<ROCKS, MULTIROCK, CAP, 3, 3, false> : k_box_step<ROCKS, MULTIROCK, CAP, 4, 3, false>);
+    auto kern2 = stages == 2 ? k_box_step<ROCKS, MULTIROCK, CAP, 2, 2, false> : (stages == 3 ? k_box_step<ROCKS, MULTIROCK, CAP, 3, 2, false> : k_box_step<ROCKS, MULTIROCK, CAP, 4, 2, false>);
+    auto kern2s = stages == 2 ? k_box_step<ROCKS, MULTIROCK, CAP, 2, 2, CAP> : k_box_step<ROCKS, MULTIROCK, CAP, 3, 2, CAP>;
+    auto kern = share ? kern2s : (two ? kern2 : kern3);
     static size_t smem_set_all[2][5] = { { 0, 0, 0, 0, 0 }, { 0, 0, 0, 0, 0 } };
-    static size_t smem_set4[5] = { 0, 0, 0, 0, 0 };
-    size_t* smem_set = minb_env == 4 ? smem_set4 : smem_set_all[two ? 1 : 0];
+    static size_t smem_set_s[5] = { 0, 0, 0, 0, 0 };
+    size_t* smem_set = share ? smem_set_s : smem_set_all[two ? 1 : 0];
     if (lay.total > smem_set[stages]) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total) != cudaSuccess) return -1;
         smem_set[stages] = lay.total;

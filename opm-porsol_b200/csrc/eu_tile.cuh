@@ -37,6 +37,7 @@ struct EuBoxDev {
     int off_bar, off_lam, off_rk, off_stage;      // byte offsets in dynamic shared memory (from the 128-aligned base)
     int lam_bytes, rk_bytes, stage_bytes;
     int off_S, off_pc, off_qg, off_T;             // inside a stage
+    int off_fx, off_fy, fx_bytes, fy_bytes;       // SHARE: two buffers each of x+ fluxes [ty][tx+1] and y+ fluxes [ty+1][tx]
     int qg_bytes, T_bytes;                        // one axis' box
     int n_flagged;                // units with a push flag (they are the first of the list)
     const unsigned short* cmask;  // per cell: record slots with faces outside the axis planes
@@ -170,7 +171,12 @@ __global__ void __launch_bounds__(256) k_box_irregular(EuGridDev g, EuTablesDev 
     }
 }
 
-template <bool ROCKS, bool MULTIROCK, bool CAP, int NS, int MINB>
+// SHARE (used with the capillary term, whose faces are expensive): every lateral face is evaluated ONCE per tile -- a
+// thread evaluates the x+, y+ and z+ faces of its cell and leaves the x+ / y+ fluxes in shared memory for its right / upper
+// neighbour; the faces on the tile's low x / y edges are evaluated by tx + ty threads on the side.  The cell of plane k is
+// then finished one step later (after the next barrier, when its neighbours' fluxes are visible): still one barrier per
+// plane, 3 + (tx + ty)/(tx ty) face evaluations per cell instead of 5.
+template <bool ROCKS, bool MULTIROCK, bool CAP, int NS, int MINB, bool SHARE>
 __global__ void __launch_bounds__(256, MINB)
 k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUtensorMap mapPc,
            const __grid_constant__ CUtensorMap mapQG, const __grid_constant__ CUtensorMap mapT,
@@ -309,6 +315,35 @@ k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUt
         }
         // ring buffers: next (plane k+1, written in phase A), cur (plane k, read in phase B), and the one in between
         int r_next = ((z0 % 3) + 3) % 3, r_cur = (r_next + 2) % 3;
+        // SHARE: the cell of the previous plane, waiting for its neighbours' fluxes
+        double p_acc = 0.0, p_S0 = 0.0, p_ipv = 0.0, p_pcs = 1.0, p_lw = 0.0, p_lo = 0.0;
+        int p_rock = 0, fpar = 0;
+        bool p_update = false;
+        auto finish_prev = [&]() {
+            // fluxes of the x- and y- faces: left by the left / lower neighbour (or the edge threads) a step ago
+            const unsigned char* fxr = base + b.off_fx + (fpar ^ 1)*b.fx_bytes;
+            const unsigned char* fyr = base + b.off_fy + (fpar ^ 1)*b.fy_bytes;
+            const double acc = p_acc + *reinterpret_cast<const double*>(fxr + (ly*txf + lx)*8)
+                                     + *reinterpret_cast<const double*>(fyr + (ly*tx + lx)*8);
+            OwnMob<false> own0;
+            own0.lw[0] = p_lw; own0.lo[0] = p_lo;
+            double pcn;
+            const int cp = c - D;
+            const double sat = finish_cell<ROCKS, MULTIROCK, CAP, false>(L, t, f, a, cp, p_S0, p_rock, own0, p_ipv, acc, pcn, true, p_pcs);
+            if (push) {
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    if (!((push >> r) & 1)) continue;
+                    const int first = (r == 0 ? slice_lo : halo.b_lo)*EU_SLICE;
+                    const int last = (r == 0 ? halo.a_hi : slice_hi)*EU_SLICE;
+                    const int d = (cp >= first && cp < last) ? halo.dst[r][cp - first] : -1;
+                    if (d >= 0) {
+                        halo.peer_S[r][d] = sat;
+                        if (CAP && halo.peer_pc[r]) halo.peer_pc[r][d] = pcn;
+                    }
+                }
+            }
+        };
         for (int k = z0 - 1; k < z1; ++k) {
             // operands of plane k that are not staged: requested now, used after the barrier
             double inv_pv = 0.0;
@@ -362,6 +397,73 @@ k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUt
             if (tid == 0 && !first_step) produce();
             first_step = false;
             // ---- phase B: faces of plane k
+            if (SHARE) {
+                unsigned char* fxw = base + b.off_fx + fpar*b.fx_bytes;
+                unsigned char* fyw = base + b.off_fy + fpar*b.fy_bytes;
+                const unsigned char* ringc = ring0 + r_cur*b.lam_bytes;
+                const unsigned char* rkc = rk0 + r_cur*b.rk_bytes;
+                if (in_tile) {
+                    if (p_update) finish_prev();
+                    const unsigned char* QG = st + b.off_qg + o_F;
+                    const unsigned char* TT = st + b.off_T + o_T;
+                    const double2 qg5 = *reinterpret_cast<const double2*>(QG + 2*b.qg_bytes);
+                    const double T5 = CAP ? *reinterpret_cast<const double*>(TT + 2*b.T_bytes) : 0.0;
+                    const double dS5 = box_face<ROCKS, MULTIROCK, CAP, true>(L, t, m, lw1, lo1, S1, pc1, rock1, qg5, T5);
+                    if (update) {
+                        // x+ and y+ faces: this cell is their lo cell
+                        const double2 ex = *reinterpret_cast<const double2*>(ringc + o_ring + E);
+                        const double2 ey = *reinterpret_cast<const double2*>(ringc + o_ring + txp*E);
+                        double2 sx = make_double2(0.0, 0.0), sy = make_double2(0.0, 0.0);
+                        double Txp = 0.0, Typ = 0.0;
+                        int rxp = 0, ryp = 0;
+                        if (CAP) {
+                            sx = *reinterpret_cast<const double2*>(ringc + oB + o_ring + E);
+                            sy = *reinterpret_cast<const double2*>(ringc + oB + o_ring + txp*E);
+                            Txp = *reinterpret_cast<const double*>(TT + 16);
+                            Typ = *reinterpret_cast<const double*>(TT + b.T_bytes + txp*8);
+                            if (MULTIROCK) { rxp = int(rkc[o_rk + 1]); ryp = int(rkc[o_rk + txp]); }
+                        }
+                        const double2 qx = *reinterpret_cast<const double2*>(QG + 16);
+                        const double2 qy = *reinterpret_cast<const double2*>(QG + b.qg_bytes + txf*16);
+                        const double dSx = box_face<ROCKS, MULTIROCK, CAP, true>(L, t, m, ex.x, ex.y, sx.x, sx.y, rxp, qx, Txp);
+                        const double dSy = box_face<ROCKS, MULTIROCK, CAP, true>(L, t, m, ey.x, ey.y, sy.x, sy.y, ryp, qy, Typ);
+                        *reinterpret_cast<double*>(fxw + (ly*txf + lx + 1)*8) = dSx;
+                        *reinterpret_cast<double*>(fyw + ((ly + 1)*tx + lx)*8) = dSy;
+                        p_acc = ((m.dS4 - dS5) - dSx) - dSy + acc_irr;
+                        p_S0 = m.S0; p_ipv = inv_pv; p_pcs = pcs; p_lw = m.lw0; p_lo = m.lo0; p_rock = m.rock0;
+                    }
+                    p_update = update;
+                    m.dS4 = dS5;
+                }
+                // the faces on the tile's low edges: thread i < tx the y- face of cell (i, 0), thread tx + j the x- face of (0, j)
+                if (tid < tx + ty && k >= z0) {
+                    const bool yedge = tid < tx;
+                    const int i = yedge ? tid : 0, j = yedge ? 0 : tid - tx;
+                    const int hi_idx = (j + 1)*txp + i + 1;                       // ring entry of the tile cell (the face's hi cell)
+                    const int lo_idx = yedge ? hi_idx - txp : hi_idx - 1;       // halo cell below / to the left (the lo cell)
+                    const double2 el = *reinterpret_cast<const double2*>(ringc + lo_idx*E);
+                    const double2 eh = *reinterpret_cast<const double2*>(ringc + hi_idx*E);
+                    MarchCarry ml;
+                    ml.lw0 = el.x; ml.lo0 = el.y; ml.S0 = 0.0; ml.pc0 = 0.0; ml.rock0 = 0; ml.dS4 = 0.0;
+                    double2 sh = make_double2(0.0, 0.0);
+                    double Tf = 0.0;
+                    int rh = 0;
+                    if (CAP) {
+                        const double2 sl = *reinterpret_cast<const double2*>(ringc + oB + lo_idx*E);
+                        sh = *reinterpret_cast<const double2*>(ringc + oB + hi_idx*E);
+                        ml.S0 = sl.x; ml.pc0 = sl.y;
+                        if (MULTIROCK) { ml.rock0 = int(rkc[lo_idx]); rh = int(rkc[hi_idx]); }
+                        Tf = yedge ? *reinterpret_cast<const double*>(st + b.off_T + b.T_bytes + i*8)
+                                   : *reinterpret_cast<const double*>(st + b.off_T + (j*txp + 1)*8);
+                    }
+                    const double2 qf = yedge ? *reinterpret_cast<const double2*>(st + b.off_qg + b.qg_bytes + i*16)
+                                             : *reinterpret_cast<const double2*>(st + b.off_qg + j*txf*16);
+                    const double dSe = box_face<ROCKS, MULTIROCK, CAP, true>(L, t, ml, eh.x, eh.y, sh.x, sh.y, rh, qf, Tf);
+                    if (yedge) *reinterpret_cast<double*>(fyw + i*8) = dSe;
+                    else       *reinterpret_cast<double*>(fxw + j*txf*8) = dSe;
+                }
+                fpar ^= 1;
+            } else
             if (in_tile) {
                 const unsigned char* QG = st + b.off_qg + o_F;
                 const unsigned char* TT = st + b.off_T + o_T;
@@ -425,6 +527,10 @@ k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUt
             if (slot == NS) { slot = 0; par ^= 1u; }
             r_cur = r_next;
             r_next = (r_next == 2) ? 0 : r_next + 1;
+        }
+        if (SHARE) {
+            __syncthreads();                                    // the last plane's fluxes are visible
+            if (in_tile && p_update) finish_prev();
         }
         if (push) {
             // all pushes of this unit are ordered before thread 0 by the block barrier; its system-scope fence is cumulative
