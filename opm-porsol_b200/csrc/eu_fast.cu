@@ -1178,10 +1178,12 @@ static int launch_box(EuBoxPlan* p, const EuGridDev& g, const EuTablesDev& t, co
     auto kern3 = stages == 2 ? k_box_step<ROCKS, MULTIROCK, CAP, 2, 3, false> : (stages == 3 ? k_box_step<ROCKS, MULTIROCK, CAP, 3, 3, false> : k_box_step<ROCKS, MULTIROCK, CAP, 4, 3, false>);
     auto kern2 = stages == 2 ? k_box_step<ROCKS, MULTIROCK, CAP, 2, 2, false> : (stages == 3 ? k_box_step<ROCKS, MULTIROCK, CAP, 3, 2, false> : k_box_step<ROCKS, MULTIROCK, CAP, 4, 2, false>);
     auto kern2s = stages == 2 ? k_box_step<ROCKS, MULTIROCK, CAP, 2, 2, CAP> : k_box_step<ROCKS, MULTIROCK, CAP, 3, 2, CAP>;
-    auto kern = share ? kern2s : (two ? kern2 : kern3);
+    auto kern4 = stages == 2 ? k_box_step<ROCKS, MULTIROCK, CAP, 2, 4, false> : k_box_step<ROCKS, MULTIROCK, CAP, 3, 4, false>;
+    auto kern = share ? kern2s : (minb_env == 4 ? kern4 : (two ? kern2 : kern3));
     static size_t smem_set_all[2][5] = { { 0, 0, 0, 0, 0 }, { 0, 0, 0, 0, 0 } };
     static size_t smem_set_s[5] = { 0, 0, 0, 0, 0 };
-    size_t* smem_set = share ? smem_set_s : smem_set_all[two ? 1 : 0];
+    static size_t smem_set4[5] = { 0, 0, 0, 0, 0 };
+    size_t* smem_set = share ? smem_set_s : (minb_env == 4 ? smem_set4 : smem_set_all[two ? 1 : 0]);
     if (lay.total > smem_set[stages]) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total) != cudaSuccess) return -1;
         smem_set[stages] = lay.total;

@@ -474,30 +474,27 @@ k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUt
                     const unsigned char* ring = ring0 + r_cur*b.lam_bytes + o_ring;
                     const unsigned char* rk = rk0 + r_cur*b.rk_bytes + o_rk;
                     double acc = m.dS4 - dS5;
-                    // lateral faces x-, x+, y-, y+: neighbour entry, face pair, T
+                    // lateral faces x-, x+, y-, y+: neighbour entry, face pair, T -- one face at a time (short live ranges:
+                    // the operands come from shared memory, their latency is covered by the other warps)
                     const int dr[4] = { -E, E, -txp*E, txp*E };
                     const int dk[4] = { -1, 1, -txp, txp };
                     const int dq[4] = { 0, 16, b.qg_bytes, b.qg_bytes + txf*16 };
                     const int dt[4] = { 8, 16, b.T_bytes, b.T_bytes + txp*8 };
-                    double lwn[4], lon[4], Sx[4], Px[4], Tx[4];
-                    double2 qg[4];
-                    int rx[4];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const double2 e = *reinterpret_cast<const double2*>(ring + dr[q]);
-                        lwn[q] = e.x; lon[q] = e.y; Sx[q] = 0.0; Px[q] = 0.0; Tx[q] = 0.0; rx[q] = 0;
+                        double2 e2 = make_double2(0.0, 0.0);
+                        double Tq = 0.0;
+                        int rq = 0;
                         if (CAP) {
-                            const double2 e2 = *reinterpret_cast<const double2*>(ring + oB + dr[q]);
-                            Sx[q] = e2.x; Px[q] = e2.y;
-                            rx[q] = MULTIROCK ? int(rk[dk[q]]) : 0;
-                            Tx[q] = *reinterpret_cast<const double*>(TT + dt[q]);
+                            e2 = *reinterpret_cast<const double2*>(ring + oB + dr[q]);
+                            rq = MULTIROCK ? int(rk[dk[q]]) : 0;
+                            Tq = *reinterpret_cast<const double*>(TT + dt[q]);
                         }
-                        qg[q] = *reinterpret_cast<const double2*>(QG + dq[q]);
+                        const double2 qgq = *reinterpret_cast<const double2*>(QG + dq[q]);
+                        if (q & 1) acc -= box_face<ROCKS, MULTIROCK, CAP, true>(L, t, m, e.x, e.y, e2.x, e2.y, rq, qgq, Tq);
+                        else       acc += box_face<ROCKS, MULTIROCK, CAP, false>(L, t, m, e.x, e.y, e2.x, e2.y, rq, qgq, Tq);
                     }
-                    acc += box_face<ROCKS, MULTIROCK, CAP, false>(L, t, m, lwn[0], lon[0], Sx[0], Px[0], rx[0], qg[0], Tx[0]);
-                    acc -= box_face<ROCKS, MULTIROCK, CAP, true>(L, t, m, lwn[1], lon[1], Sx[1], Px[1], rx[1], qg[1], Tx[1]);
-                    acc += box_face<ROCKS, MULTIROCK, CAP, false>(L, t, m, lwn[2], lon[2], Sx[2], Px[2], rx[2], qg[2], Tx[2]);
-                    acc -= box_face<ROCKS, MULTIROCK, CAP, true>(L, t, m, lwn[3], lon[3], Sx[3], Px[3], rx[3], qg[3], Tx[3]);
                     acc += acc_irr;
                     OwnMob<false> own0;
                     own0.lw[0] = m.lw0; own0.lo[0] = m.lo0;
