@@ -464,8 +464,8 @@ def main():
                        "parallelism": f"z-slabs x{world}", "arithmetic_mode": a.mode,
                        "l2": "inputs (>= 1 GB per substep and GPU) exceed the 126 MB L2; no flush needed",
                        "setup_s": round(t_setup, 1), "sat_range_after": [s_min, s_max],
-                       "kernel_path": "box kernel (TMA-staged plane sweep)" if plan["class_fraction"] == 1.0 and plan["max_march"] > 1
-                                      else "slice-class kernel", "work_units": plan["items"], "planes_per_unit": plan["mean_march"]},
+                       "kernel_path": "box kernel (TMA-staged plane sweep)" if plan["kernel"] == "box" else "slice-class kernel",
+                       "work_units": plan["items"], "planes_per_unit": plan["mean_march"]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved/peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "kernel": "k_box_step (+ k_box_irregular pre-pass)" if a.mode != "strict" else "k_strict_step",

@@ -183,9 +183,9 @@ double eu_regular_fraction(eu_handle h);
  * STRICT mode): out[0] = fraction of the own slices (32 cells) that belong to a slice class, out[1] = number of work
  * items, out[2] = longest march (slices per item), out[3] = mean march length over the class items.  When the box
  * kernel ran (local numbering c = x + nx*(y + ny*z): tiles swept along z with TMA-staged operands) out[0] = 1, out[1] =
- * work units (tile x z-chunk), out[2], out[3] = planes per unit.  Tests use it to assert which code path a parity case
- * exercised; EU_BOX=0 in the environment keeps the slice-class kernel. */
-int eu_work_plan(eu_handle h, double out[4]);
+ * work units (tile x z-chunk), out[2], out[3] = planes per unit; out[4] = 1 when the box kernel ran, else 0.  Tests use it
+ * to assert which code path a parity case exercised; EU_BOX=0 in the environment keeps the slice-class kernel. */
+int eu_work_plan(eu_handle h, double out[5]);
 
 /* ---- EulerUpstream::transportSolve (EulerUpstream_impl.hpp:151-218) -------------------
  * saturation:  local cells (in/out; ghost entries are inputs only)

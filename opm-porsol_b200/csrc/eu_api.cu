@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <unistd.h>
 #include <limits>
 #include <map>
 #include <algorithm>
@@ -1376,9 +1377,10 @@ int eu_local_cells(eu_handle h) { return h ? h->n_local : 0; }
 int eu_resolved_mode(eu_handle h) { return (h && h->grid_ready) ? h->mode : EU_MODE_AUTO; }
 double eu_regular_fraction(eu_handle h) { return h ? h->regular_fraction : 0.0; }
 long long eu_local_halffaces(eu_handle h) { return h ? h->H : 0; }
-int eu_work_plan(eu_handle h, double out[4])
+int eu_work_plan(eu_handle h, double out[5])
 {
     if (!h || !out) return EU_ERR_ARG;
+    out[4] = 0.0;
     if (h->mode == EU_MODE_FAST && h->ran_box && h->box) {
         // box kernel: every own cell is swept by a tile; items = work units, march = planes per unit
         int info[6];
@@ -1389,6 +1391,7 @@ int eu_work_plan(eu_handle h, double out[4])
         const int tiles = ((h->axis[1] + info[0] - 1)/info[0])*((h->axis[2]/h->axis[1] + info[1] - 1)/info[1]);
         out[3] = info[2] > 0 ? double(planes)*tiles/double(info[2]) : 0.0;
         out[2] = std::ceil(out[3]);
+        out[4] = 1.0;
         return EU_OK;
     }
     const bool have = h->mode == EU_MODE_FAST && h->items_lo >= 0;
@@ -1806,6 +1809,11 @@ void eu_host_unpin_all(eu_handle h) { if (h) { cudaSetDevice(h->cfg.device); cud
 struct EuBlobHeader {
     int magic, rank, world, own_begin, own_end, n_ghost;
     cudaIpcMemHandle_t mem[5];       // S[0], S[1], pc[0], pc[1], flags
+    // ranks of ONE process (one solver per GPU, the C++ drop-in with several devices): CUDA IPC does not open a handle in
+    // the process that exported it; peers there use the device pointers directly, with peer access enabled
+    long long pid;
+    int device, pad;
+    void* raw[5];
 };
 
 int eu_comm_plan_sends(int own_begin, int own_end, int n_ghost, const int* ghost_global, const int* ghost_local,
@@ -1856,6 +1864,9 @@ int eu_comm_export(eu_handle h, void* blob)
     hd.own_begin = h->cfg.own_begin; hd.own_end = h->cfg.own_end; hd.n_ghost = int(h->ghost_global.size());
     void* ptrs[5] = { h->d_S[0].p, h->d_S[1].p, h->d_pc[0].p, h->d_pc[1].p, h->d_comm_flags.p };
     for (int k = 0; k < 5; ++k) EU_CUDA(h, cudaIpcGetMemHandle(&hd.mem[k], ptrs[k]));
+    hd.pid = (long long)getpid();
+    hd.device = h->cfg.device;
+    for (int k = 0; k < 5; ++k) hd.raw[k] = ptrs[k];
     char* out = static_cast<char*>(blob);
     std::memcpy(out, &hd, sizeof(hd));
     std::memcpy(out + sizeof(hd), h->ghost_global.data(), sizeof(int)*h->ghost_global.size());
@@ -1892,14 +1903,30 @@ int eu_comm_connect(eu_handle h, int n_blobs, const void* const* blobs, const in
         eu_solver::Peer* p = new eu_solver::Peer;
         h->peers.push_back(p);
         p->rank = r; p->recv = recv; p->n_send = n_send;
-        for (int k = 0; k < 5; ++k) {
-            cudaError_t e = cudaIpcOpenMemHandle(&p->opened[k], hd.mem[k], cudaIpcMemLazyEnablePeerAccess);
-            if (e != cudaSuccess)
-                return fail(h, EU_ERR_COMM, std::string("cudaIpcOpenMemHandle (peer-to-peer access to the neighbour rank): ") + cudaGetErrorString(e));
+        void* mapped[5];
+        if (hd.pid == (long long)getpid()) {
+            // same process: the peer's buffers are plain device pointers once peer access is on
+            if (hd.device != h->cfg.device) {
+                int can = 0;
+                cudaDeviceCanAccessPeer(&can, h->cfg.device, hd.device);
+                if (!can) return fail(h, EU_ERR_COMM, "no peer-to-peer access between the devices of this process");
+                cudaError_t e = cudaDeviceEnablePeerAccess(hd.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                    return fail(h, EU_ERR_COMM, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+                cudaGetLastError();
+            }
+            for (int k = 0; k < 5; ++k) mapped[k] = hd.raw[k];
+        } else {
+            for (int k = 0; k < 5; ++k) {
+                cudaError_t e = cudaIpcOpenMemHandle(&p->opened[k], hd.mem[k], cudaIpcMemLazyEnablePeerAccess);
+                if (e != cudaSuccess)
+                    return fail(h, EU_ERR_COMM, std::string("cudaIpcOpenMemHandle (peer-to-peer access to the neighbour rank): ") + cudaGetErrorString(e));
+                mapped[k] = p->opened[k];
+            }
         }
-        p->S[0] = static_cast<double*>(p->opened[0]); p->S[1] = static_cast<double*>(p->opened[1]);
-        p->pc[0] = static_cast<double*>(p->opened[2]); p->pc[1] = static_cast<double*>(p->opened[3]);
-        p->flags = static_cast<unsigned*>(p->opened[4]);
+        p->S[0] = static_cast<double*>(mapped[0]); p->S[1] = static_cast<double*>(mapped[1]);
+        p->pc[0] = static_cast<double*>(mapped[2]); p->pc[1] = static_cast<double*>(mapped[3]);
+        p->flags = static_cast<unsigned*>(mapped[4]);
         if (n_send > 0) {
             std::vector<int> src(static_cast<size_t>(n_send), 0);
             std::vector<int> dst(sl.begin(), sl.begin() + n_send);

@@ -934,6 +934,8 @@ struct EuBoxPlan {
     int n_units = 0, n_bnd_units[2] = { 0, 0 }, n_flagged = 0;
     int units_key[5] = { -1, -1, -1, -1, -1 };      // (bnd planes lo, hi, grid blocks, lz override, cap) the unit list was built for
     const unsigned short* cmask = nullptr;
+    size_t smem_set[32] = { 0 };
+    int blocks_per_sm[32] = { 0 };
     const int* irr_cells = nullptr;
     int n_irr = 0;
     double* acc_irr = nullptr;
@@ -1180,16 +1182,20 @@ static int launch_box(EuBoxPlan* p, const EuGridDev& g, const EuTablesDev& t, co
     auto kern2s = stages == 2 ? k_box_step<ROCKS, MULTIROCK, CAP, 2, 2, CAP> : k_box_step<ROCKS, MULTIROCK, CAP, 3, 2, CAP>;
     auto kern4 = stages == 2 ? k_box_step<ROCKS, MULTIROCK, CAP, 2, 4, false> : k_box_step<ROCKS, MULTIROCK, CAP, 3, 4, false>;
     auto kern = share ? kern2s : (minb_env == 4 ? kern4 : (two ? kern2 : kern3));
-    static size_t smem_set_all[2][5] = { { 0, 0, 0, 0, 0 }, { 0, 0, 0, 0, 0 } };
-    static size_t smem_set_s[5] = { 0, 0, 0, 0, 0 };
-    static size_t smem_set4[5] = { 0, 0, 0, 0, 0 };
-    size_t* smem_set = share ? smem_set_s : (minb_env == 4 ? smem_set4 : smem_set_all[two ? 1 : 0]);
-    if (lay.total > smem_set[stages]) {
+    // function attributes are per device: a plan remembers what it set on ITS device (several solvers, one per GPU, may
+    // live in one process)
+    const int vkey = (share ? 16 : 0) + (minb_env == 4 ? 8 : 0) + (two ? 4 : 0) + stages - 2;
+    if (lay.total > p->smem_set[vkey]) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total) != cudaSuccess) return -1;
-        smem_set[stages] = lay.total;
+        p->smem_set[vkey] = lay.total;
+        p->blocks_per_sm[vkey] = 0;
     }
-    int blocks_per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, p->threads, lay.total);
+    if (p->blocks_per_sm[vkey] == 0) {
+        int bps = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, p->threads, lay.total);
+        p->blocks_per_sm[vkey] = bps;
+    }
+    const int blocks_per_sm = p->blocks_per_sm[vkey];
     if (blocks_per_sm < 1) return -1;
     const int grid_full = p->n_sms*blocks_per_sm;
     if (box_build_units(p, bnd_lo, bnd_hi, grid_full, CAP)) return -1;
@@ -1252,8 +1258,14 @@ template <bool ROCKS, bool MULTIROCK, bool CAP, bool NN, int B6, int B8, int MIN
 static void launch_variant(const EuGridDev& g, const EuTablesDev& t, const EuFastDev& f, const EuStepArgs& a,
                            const EuHaloDev& halo, int slice_lo, int slice_hi, int n_sms, size_t smem_tables, cudaStream_t st)
 {
-    static int blocks_per_sm = 0;
-    static size_t smem_seen = 0;
+    // per device (function attributes are per device; several solvers, one per GPU, may live in one process)
+    static int blocks_per_sm_dev[64] = { 0 };
+    static size_t smem_seen_dev[64] = { 0 };
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    int& blocks_per_sm = blocks_per_sm_dev[dev];
+    size_t& smem_seen = smem_seen_dev[dev];
     auto kern = k_fast_step<ROCKS, MULTIROCK, CAP, NN, B6, B8, MINB, TENSOR>;
     // shared memory: rock tables | slice classes
     const size_t smem = smem_tables + sizeof(EuSliceClass)*EU_MAX_CLASSES;

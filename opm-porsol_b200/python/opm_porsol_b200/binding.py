@@ -398,9 +398,10 @@ class EulerUpstream:
 
     def work_plan(self):
         """Work plan of the FAST substep kernel after the last substep: class fraction, items, longest / mean march."""
-        out = np.zeros(4)
+        out = np.zeros(5)
         self._check(self.L.eu_work_plan(self.h, _d(out)))
-        return {"class_fraction": float(out[0]), "items": int(out[1]), "max_march": int(out[2]), "mean_march": float(out[3])}
+        return {"class_fraction": float(out[0]), "items": int(out[1]), "max_march": int(out[2]), "mean_march": float(out[3]),
+                "kernel": "box" if out[4] == 1.0 else "slice-class"}
 
     def cfl_times(self, gravity):
         g = np.ascontiguousarray(gravity, dtype=np.float64)

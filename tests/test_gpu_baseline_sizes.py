@@ -1,5 +1,6 @@
 """GPU parity against the CPU ORACLE (not against the device's own STRICT mode) at the BASELINE.json sizes and on the
-code path bench.py times: the z-march of the FAST kernel with the carried face flux.
+code path bench.py times: the box kernel of FAST mode (TMA-staged plane sweep over tiles, eu_tile.cuh) -- and, with
+EU_BOX=0, the slice-class kernel with its z-march that it replaced and that still serves grids without a box numbering.
 
   C4 slab  512 x 512 x 4 and 64 x 32 x 8, viscous + gravity, 1 rock   (the bench workload's plane shape)
   C2       100^3, rotated anisotropic K, rock table, capillary on       (BASELINE config 1, full size)
@@ -68,9 +69,12 @@ def _device_check(case, ref, mode, expect_march):
         dev.upload_saturation(sat_ref)            # every substep is an independent comparison
     if mode == "fast" and expect_march:
         plan = dev.work_plan()
-        # the march with the carried face flux is what ran: (nearly) all slices in classes, items longer than one slice
-        assert plan["class_fraction"] > 0.7, plan
-        assert plan["max_march"] >= 1, plan
+        if expect_march == "box":
+            # the box kernel is what ran: every own cell swept by a tile, units longer than one plane
+            assert plan["kernel"] == "box" and plan["items"] > 0, plan
+        else:
+            # EU_BOX=0: the slice-class kernel; its marches need slice-aligned planes
+            assert plan["kernel"] == "slice-class" and plan["class_fraction"] > 0.5 and plan["max_march"] >= 1, plan
     sol = ref["sol"]
     if sol is not None:
         sat = case.sat0.copy()
@@ -86,13 +90,16 @@ def _device_check(case, ref, mode, expect_march):
 
 
 @pytest.mark.parametrize("dims", [(64, 32, 8), (512, 512, 4)], ids=["64x32x8", "512x512x4"])
-def test_c4_slab_march_path_vs_oracle(dims):
-    """The bench workload's kernel instantiation (1 rock, no capillary term, march along z) against the oracle."""
+def test_c4_slab_march_path_vs_oracle(dims, monkeypatch):
+    """The bench workload's kernel instantiation (1 rock, no capillary term, sweep along z) against the oracle: the box
+    kernel (default) and the slice-class kernel (EU_BOX=0)."""
     from opm_porsol_b200 import synth
     case = synth.config_c4(*dims)
     ref = _oracle_run(case, n_sub=4, solve_steps=18 if dims[0] < 512 else 6)
     for mode in ("fast", "strict"):
-        _device_check(case, ref, mode, expect_march=True)
+        _device_check(case, ref, mode, expect_march="box")
+    monkeypatch.setenv("EU_BOX", "0")
+    _device_check(case, ref, "fast", expect_march="classes")
 
 
 def test_c4_slab_capillary_march_vs_oracle():
@@ -101,7 +108,7 @@ def test_c4_slab_capillary_march_vs_oracle():
     case = synth.config_c4(256, 128, 6, capillary=True)
     ref = _oracle_run(case, n_sub=3, solve_steps=8)
     for mode in ("fast", "strict"):
-        _device_check(case, ref, mode, expect_march=True)
+        _device_check(case, ref, mode, expect_march="box")
 
 
 def test_c2_full_size_vs_oracle():
@@ -109,7 +116,7 @@ def test_c2_full_size_vs_oracle():
     from opm_porsol_b200 import synth
     case = synth.config_c2(100)
     ref = _oracle_run(case, n_sub=3, solve_steps=18, cfl_fraction=0.25)
-    _device_check(case, ref, "fast", expect_march=False)
+    _device_check(case, ref, "fast", expect_march="box")          # 100 x 100 planes: no slice alignment needed
     _device_check(case, ref, "strict", expect_march=False)
 
 
@@ -119,5 +126,5 @@ def test_c3_full_size_vs_oracle():
     from opm_porsol_b200 import synth
     case = synth.config_c3(256, 256, 128)
     ref = _oracle_run(case, n_sub=2, solve_steps=0, cfl_fraction=0.25)
-    _device_check(case, ref, "fast", expect_march=True)
+    _device_check(case, ref, "fast", expect_march="box")          # fault faces through the pre-pass kernel
     _device_check(case, ref, "strict", expect_march=False)

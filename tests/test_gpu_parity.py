@@ -179,3 +179,20 @@ def test_failure_after_ten_retries_reports_reference_message():
         assert abs(rep.bad_value - a["bad_value"]) <= (0.0 if mode == "strict" else 1e-9)
         assert rep.substeps_executed >= a["substeps_executed"]
         dev.close()
+
+
+@pytest.mark.parametrize("name,case", small_cases(), ids=[n for n, _ in small_cases()])
+def test_slice_class_kernel_still_matches(name, case, monkeypatch):
+    """EU_BOX=0: the slice-class kernel (warp marches, generic gather) that the box kernel replaced on box-numbered grids
+    and that still serves every other grid: the same per-transportSolve gate."""
+    monkeypatch.setenv("EU_BOX", "0")
+    dev, port = _solvers(case, "fast")
+    total = active_cfl_dt(case, port.cfl_times())
+    time = 17.3*total
+    a = port.transport_solve(case.sat0, time=time)
+    sat = case.sat0.copy()
+    rep = dev.transportSolve(sat, time, case.gravity, case.hf_flux, (case.src_cell, case.src_rate))
+    assert rep.nsteps == a["nsteps"] == 18 and rep.attempts == a["attempts"]
+    assert np.abs(sat - a["sat"]).max() <= TOL_SOLVE
+    assert dev.work_plan()["kernel"] == "slice-class"
+    dev.close()
