@@ -283,6 +283,7 @@ k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUt
         for (int j = 0; j < NS; ++j) produce();
     }
     bool first_step = true;                                     // nothing to refill at the block's very first step
+    unsigned done0 = 0u, done1 = 0u;                            // finished units of this block with pushes to range A / B
 
     for (int u = blockIdx.x; u < b.n_units; u += gridDim.x) {
         const int4 unit = __ldg(b.units + u);
@@ -530,15 +531,21 @@ k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUt
             if (in_tile && p_update) finish_prev();
         }
         if (push) {
-            // all pushes of this unit are ordered before thread 0 by the block barrier; its system-scope fence is cumulative
-            // (one fence per unit instead of one per thread), then the finished-unit counters of the unit's ranges
+            if (push & 1) ++done0;
+            if (push & 2) ++done1;
+        }
+        if ((done0 | done1) && u + int(gridDim.x) >= b.n_flagged) {
+            // this was the block's last unit with pushes (they are the first of the list): all of them are ordered
+            // before thread 0 by the block barrier, its ONE system-scope fence is cumulative, then the finished-unit
+            // counters of the two ranges (a fence per unit held the whole block back for its NVLink round trip)
             __syncthreads();
             if (tid == 0) {
                 __threadfence_system();
+                const unsigned dn[2] = { done0, done1 };
                 for (int r = 0; r < 2; ++r) {
-                    if (!((push >> r) & 1)) continue;
-                    const unsigned before = atomicAdd(halo.counter[r], 1u);
-                    if (before + 1u == halo.total[r]) {
+                    if (dn[r] == 0u) continue;
+                    const unsigned before = atomicAdd(halo.counter[r], dn[r]);
+                    if (before + dn[r] == halo.total[r]) {
                         *halo.counter[r] = 0u;
                         __threadfence_system();
                         *(volatile unsigned*)halo.peer_flag[r] = halo.epoch;
@@ -546,6 +553,7 @@ k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUt
                     }
                 }
             }
+            done0 = done1 = 0u;
         }
     }
 }
