@@ -153,6 +153,8 @@ typedef struct eu_report {
 
 /* ---- life cycle ------------------------------------------------------------------------ */
 int eu_create(const eu_config* cfg, eu_handle* out);
+/* number of CUDA devices this process sees (0 without a driver / device) */
+int eu_device_count(void);
 void eu_destroy(eu_handle h);
 const char* eu_last_error(eu_handle h);     /* h may be NULL: error of the last failed eu_create */
 int eu_abi_version(void);

@@ -869,6 +869,13 @@ void eu_default_params(eu_params* p)
 
 const char* eu_last_error(eu_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
+int eu_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
 int eu_create(const eu_config* cfg, eu_handle* out)
 {
     if (!cfg || !out) return fail(nullptr, EU_ERR_ARG, "null argument");
@@ -1740,7 +1747,12 @@ int eu_transport_solve_resident(eu_handle h, double time, const double gravity[3
             // encode as max over (large - substep) so that the earliest failure wins
             double enc = key == none ? 0.0 : 4294967296.0 - k;
             h->allreduce(h->allreduce_user, &enc, 1, 1);
-            if (enc != 0.0 && key == none) key = (unsigned long long)(4294967296.0 - enc) << 32 | 0xffffffffu;
+            // the attempt failed in substep `first` somewhere; a rank whose own first failure came later (or never) has
+            // no cell to report for it -- the reference stops at the lowest failing cell of that substep
+            if (enc != 0.0) {
+                const unsigned long long first = (unsigned long long)(4294967296.0 - enc);
+                if (key == none || (key >> 32) > first) key = first << 32 | 0xffffffffu;
+            }
         }
         if (key == none) {
             finished = true;

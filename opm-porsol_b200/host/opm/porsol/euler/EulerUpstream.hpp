@@ -31,11 +31,13 @@
 
 #include <euler_b200.h>
 
+#include <cstdlib>
 #include <iostream>
 #include <stdexcept>
 #include <string>
 #include <type_traits>
 #include <utility>
+#include <vector>
 #include <vector>
 
 namespace Opm {
@@ -55,8 +57,9 @@ namespace b200 {
         EulerUpstream(const EulerUpstream&) = delete;
         EulerUpstream& operator=(const EulerUpstream&) = delete;
 
-        /// Same keys and defaults as the reference (EulerUpstream_impl.hpp:95-108), plus two optional ones:
-        /// b200_device (CUDA ordinal, default 0) and b200_mode (0 auto, 1 strict = bit-identical, 2 fast).
+        /// Same keys and defaults as the reference (EulerUpstream_impl.hpp:95-108), plus three optional ones:
+        /// b200_device (CUDA ordinal, default 0), b200_devices (comma-separated ordinals: the grid is split into slabs over
+        /// these devices of the process) and b200_mode (0 auto, 1 strict = bit-identical, 2 fast).
         void init(const Opm::parameter::ParameterGroup& param)
         {
             par_.courant_number = param.getDefault("courant_number", par_.courant_number);
@@ -72,7 +75,17 @@ namespace b200 {
             par_.clamp_sat = param.getDefault("clamp_sat", par_.clamp_sat != 0);
             device_ = param.getDefault("b200_device", device_);
             mode_ = param.getDefault("b200_mode", mode_);
-            if (model_.ready()) eu_set_params(model_.handle(), &par_);
+            // b200_devices=0,1,..: several devices of this process, the grid split into slabs of contiguous cell indices
+            const std::string list = param.getDefault("b200_devices", std::string());
+            devices_.clear();
+            for (std::string::size_type p = 0; p < list.size();) {
+                const std::string::size_type q = list.find(',', p);
+                const std::string tok = list.substr(p, q == std::string::npos ? std::string::npos : q - p);
+                if (!tok.empty()) devices_.push_back(std::atoi(tok.c_str()));
+                if (q == std::string::npos) break;
+                p = q + 1;
+            }
+            if (model_.ready()) model_.setParams(par_);
         }
 
         void init(const Opm::parameter::ParameterGroup& param, const GridInterface& grid,
@@ -84,7 +97,8 @@ namespace b200 {
 
         void initObj(const GridInterface& grid, const ReservoirProperties& resprop, const BoundaryConditions& boundary)
         {
-            model_.create(device_, mode_, par_, grid, resprop, boundary, "EulerUpstream");
+            if (devices_.size() > 1) model_.create(devices_, mode_, par_, grid, resprop, boundary, "EulerUpstream");
+            else model_.create(devices_.empty() ? device_ : devices_[0], mode_, par_, grid, resprop, boundary, "EulerUpstream");
         }
 
         void display()
@@ -99,7 +113,7 @@ namespace b200 {
         void setCourantNumber(double cn)
         {
             par_.courant_number = cn;
-            if (model_.ready()) eu_set_params(model_.handle(), &par_);
+            if (model_.ready()) model_.setParams(par_);
         }
 
         /// Report of the last transportSolve (step count, retries, CFL times, device time).
@@ -117,8 +131,7 @@ namespace b200 {
             std::vector<double> src_rate;
             Model::sources(injection_rates, src_cell, src_rate);
             const double g[3] = { gravity[0], gravity[1], gravity[2] };
-            const int rc = eu_transport_solve(model_.handle(), saturation.data(), time, g, model_.fluxes().data(),
-                                              int(src_cell.size()), src_cell.data(), src_rate.data(), &report_);
+            const int rc = model_.transportSolve(saturation, time, g, src_cell, src_rate, &report_);
             for (int r = 1; r < report_.attempts; ++r) {
                 OPM_MESSAGE("Warning: Transport failed, retrying with more steps.");
             }
@@ -129,7 +142,7 @@ namespace b200 {
             if (rc == EU_ERR_CFL_ZERO) {
                 OPM_THROW(std::runtime_error, "Cfl computation gave dt = 0.0");
             }
-            model_.check(rc, "EulerUpstream");
+            if (rc != EU_OK) OPM_THROW(std::runtime_error, "EulerUpstream (B200): " << model_.lastError());
         }
 
         /// The device solver behind this object (C ABI handle), e.g. for the diagnostics of euler_b200.h.
@@ -141,6 +154,7 @@ namespace b200 {
         mutable Model model_;
         eu_params par_;
         int device_;
+        std::vector<int> devices_;
         int mode_;
         mutable eu_report report_;
     };

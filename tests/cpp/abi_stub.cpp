@@ -140,3 +140,12 @@ int eu_phase_velocities(eu_handle, const double*, const double* cv, double* vw, 
 int eu_fractional_flow(eu_handle, const double* s, double* f) { for (int i = 0; i < g_rec.n_local; ++i) f[i] = 0.5*s[i]; return EU_OK; }
 
 } // extern "C"
+
+// multi-device plumbing: the CPU tests run the drop-in with one device only; these are never called there
+extern "C" {
+int eu_device_count(void) { return 1; }
+int eu_comm_blob_size(eu_handle) { return 0; }
+int eu_comm_export(eu_handle, void*) { return EU_ERR_UNSUPPORTED; }
+int eu_comm_connect(eu_handle, int, const void* const*, const int*) { return EU_ERR_UNSUPPORTED; }
+int eu_comm_set_allreduce(eu_handle, eu_allreduce_fn, void*) { return EU_ERR_UNSUPPORTED; }
+}

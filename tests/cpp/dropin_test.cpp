@@ -10,7 +10,7 @@
 
 template <class RP, class Flux>
 static int runCase(const char* name, int nx, int ny, int nz, int n_rocks, bool aniso, bool periodic_x, int mode,
-                   double tol, const std::string& dir, bool expect_failure)
+                   double tol, const std::string& dir, bool expect_failure, const char* devices = 0)
 {
     Rng rng(12345 + nx*7 + ny*13 + nz*31 + n_rocks);
     GI grid;
@@ -37,6 +37,7 @@ static int runCase(const char* name, int nx, int ny, int nz, int n_rocks, bool a
     Opm::parameter::ParameterGroup param;
     param.insertParameter("maximum_small_steps", expect_failure ? 2 : 40);
     param.insertParameter("b200_mode", mode);
+    if (devices) param.insertParameter("b200_devices", std::string(devices));      // several devices of this process
     Opm::EulerUpstream<GI, RP, BCs> ref;
     ref.init(param, grid, rp, bc);
     Opm::b200::EulerUpstream<GI, RP, BCs> dev;
@@ -150,6 +151,14 @@ int main(int argc, char** argv)
     bad += runCase<RPA, FlatFlux>("tensor 2 rocks periodic auto=fast", 5, 4, 3, 2, true, true, 0, 1e-9, dir, false);
     bad += runCase<RPS, IterFlux>("failure after 10 retries strict", 5, 4, 3, 1, false, false, 1, 0.0, dir, true);
     bad += runCase<RPS, IterFlux>("failure after 10 retries fast", 5, 4, 3, 1, false, false, 2, 0.0, dir, true);
+    if (eu_device_count() >= 2) {
+        // the grid split into two slabs over two devices of this process: STRICT stays bit-identical to the reference
+        bad += runCase<RPS, IterFlux>("2 devices: scalar 2 rocks strict", 7, 5, 8, 2, false, true, 1, 0.0, dir, false, "0,1");
+        bad += runCase<RPS, FlatFlux>("2 devices: scalar 3 rocks fast", 16, 4, 12, 3, false, false, 2, 1e-9, dir, false, "0,1");
+        bad += runCase<RPS, IterFlux>("2 devices: failure strict", 5, 4, 6, 1, false, false, 1, 0.0, dir, true, "0,1");
+    } else {
+        std::printf("(one device: the 2-device cases are skipped)\n");
+    }
     bad += runResidualCase<RPS, IterFlux>("residual scalar 2 rocks strict", 6, 5, 4, 2, false, true, 1, 0.0, dir);
     bad += runResidualCase<RPS, FlatFlux>("residual scalar 3 rocks fast", 6, 5, 4, 3, false, false, 2, 1e-12, dir);
     bad += runResidualCase<RPS, IterFlux>("residual scalar no rocks auto", 5, 4, 4, 0, false, true, 0, 1e-12, dir);
