@@ -298,6 +298,21 @@ int eu_compute_cfl_factors(const eu_fluid* fluid, int n_cells, const double* por
 int eu_match_periodic_faces(int n, const double* centroid, const double* area, const int is_periodic[6],
                             double spatial_tolerance, int* canon_pos, int* partner, double side_areas[6]);
 
+/* ---- host-side helpers for the callers and data formats on either side of the path (no device needed) -----------
+ * eu_build_face_indices: GridInterfaceEuler::buildFaceIndices (common/GridInterfaceEuler.hpp:498-611) over the flat CSR
+ *      adjacency (hf_neighbour < 0 = boundary): unique face number per half-face -- interior faces in the order the
+ *      cell walk discovers them, boundary faces after them; out: face_index[H], *num_faces, *max_faces_per_cell.
+ * eu_post_process_fluxes: IncompFlowSolverHybrid::postProcessFluxes (mimetic/IncompFlowSolverHybrid.hpp:707-807): makes
+ *      the out-fluxes of the two half-faces of a face exactly antisymmetric (periodic partners via partner_face[face],
+ *      -1 or NULL = none), in place; *max_modification = the largest change.  Produces the hf_flux array that
+ *      eu_transport_solve consumes.
+ * eu_write_field: writeField (common/SimulatorUtilities.hpp:288-298), the per-step saturation file of the drivers. */
+int eu_build_face_indices(int n_cells, const int* hf_offset, const int* hf_neighbour, int* face_index, int* num_faces,
+                          int* max_faces_per_cell);
+int eu_post_process_fluxes(int n_cells, const int* hf_offset, const int* hf_neighbour, const int* face_index, int num_faces,
+                           const int* partner_face, double* hf_flux, double* max_modification);
+int eu_write_field(const double* field, long long n, const char* filename);
+
 #ifdef __cplusplus
 }
 #endif

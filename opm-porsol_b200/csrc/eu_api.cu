@@ -9,6 +9,8 @@
 // The arithmetic runs in the kernels of eu_setup.cu (STRICT, setup, CFL) and eu_fast.cu (FAST).
 #include "eu_internal.h"
 
+#include <nvtx3/nvToolsExt.h>     // header-only NVTX v3: ranges show up in Nsight Systems / ncu --nvtx, no-ops otherwise
+
 #include <algorithm>
 #include <climits>
 #include <cmath>
@@ -23,6 +25,13 @@
 #include <vector>
 
 namespace {
+
+// NVTX range over a scope (the reference has its own StopWatch prints around the same phases,
+// EulerUpstream_impl.hpp:185-186,214-217)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 std::string g_create_error;
 
@@ -1157,6 +1166,7 @@ int eu_set_fluid(eu_handle h, const eu_fluid* f)
 int eu_grid_end(eu_handle h)
 {
     if (!h) return EU_ERR_ARG;
+    NvtxRange nvtx_end("eu_grid_end (structure building)");
     if (!h->grid_open) return fail(h, EU_ERR_ARG, "eu_grid_end before eu_grid_begin");
     if (!h->fluid_set) return fail(h, EU_ERR_ARG, "eu_set_fluid must precede eu_grid_end");
     if (h->n_local != h->n_local_expected || h->H != h->H_expected) return fail(h, EU_ERR_ARG, "fewer cells/half-faces than announced");
@@ -1673,8 +1683,12 @@ int eu_transport_solve_resident(eu_handle h, double time, const double gravity[3
     // ---- computeCflTime (EulerUpstream_impl.hpp:263-331)
     int zero = 0;
     double cfl[3];
-    if ((rc = compute_cfl(h, gravity, p.method_viscous && p.use_cfl_viscous, p.method_gravity && p.use_cfl_gravity,
-                          p.method_capillary && p.use_cfl_capillary, cfl, &zero, &launches))) return rc;
+    NvtxRange nvtx_solve("eu_transport_solve_resident");
+    nvtxRangePushA("eu: computeCflTime + flux compaction");
+    rc = compute_cfl(h, gravity, p.method_viscous && p.use_cfl_viscous, p.method_gravity && p.use_cfl_gravity,
+                     p.method_capillary && p.use_cfl_capillary, cfl, &zero, &launches);
+    nvtxRangePop();
+    if (rc) return rc;
     rep->cfl_dt[0] = cfl[0]; rep->cfl_dt[1] = cfl[1]; rep->cfl_dt[2] = cfl[2];
     if (zero && p.method_viscous && p.use_cfl_viscous) {
         rep->status = EU_ERR_CFL_ZERO;
@@ -1716,6 +1730,7 @@ int eu_transport_solve_resident(eu_handle h, double time, const double gravity[3
             if ((rc = build_items(h, fused ? h->fused_a_hi : h->own_lo/EU_SLICE,
                                   fused ? h->fused_b_lo : (h->own_hi + EU_SLICE - 1)/EU_SLICE))) return rc;
         }
+        NvtxRange nvtx_attempt("eu: substep loop (one attempt)");
         EU_CUDA(h, cudaEventRecord(h->ev0, h->st));
         for (int q = 0; q < nsteps; ++q) {
             EuStepArgs a = step_args(h, dt, gravity, nls, q);
@@ -1802,6 +1817,7 @@ int eu_transport_solve(eu_handle h, double* saturation, double time, const doubl
 {
     if (!h || !saturation || !hf_flux || !report) return EU_ERR_ARG;
     int rc;
+    NvtxRange nvtx_all("eu_transport_solve (H2D + solve + D2H)");
     if ((rc = eu_upload_state(h, saturation, hf_flux))) return rc;
     rc = eu_transport_solve_resident(h, time, gravity, n_src, src_cell, src_rate, report);
     if (rc != EU_OK && rc != EU_ERR_SAT_RANGE) return rc;

@@ -8,6 +8,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <fstream>
+#include <iterator>
 #include <vector>
 
 namespace {
@@ -178,3 +180,121 @@ extern "C" int eu_match_periodic_faces(int n, const double* centroid, const doub
     }
     return EU_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Callers and data formats on either side of the path, host only.
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+// GridInterfaceEuler::buildFaceIndices (common/GridInterfaceEuler.hpp:498-611) over the flat CSR adjacency: unique face
+// numbers per half-face.  Interior faces are numbered in the order the cell walk discovers them (a face is discovered by
+// the cell visited first, :531-541), boundary faces after all interior ones in walk order (:573-575); a half-face of
+// the later cell finds its number by the FIRST entry of the earlier cell's discovered faces that names it (:588-593,
+// std::find -- two faces between the same pair of cells share the first one's number, as in the reference).  The
+// reference's search walks a growing table (its comment: "potentially *VERY* expensive"); here each cell's discovered
+// faces are a short contiguous range, O(half-faces x faces per cell).  Cell index == iteration order (as for CpGrid).
+int eu_build_face_indices(int n_cells, const int* hf_offset, const int* hf_neighbour, int* face_index, int* num_faces,
+                          int* max_faces_per_cell)
+{
+    if (n_cells < 0 || !hf_offset || !hf_neighbour || !face_index) return EU_ERR_ARG;
+    std::vector<int> faces;                       // neighbour cell of every discovered interior face
+    std::vector<int> fpos(size_t(n_cells) + 1, 0);
+    int max_ncf = 0;
+    for (int c = 0; c < n_cells; ++c) {           // first pass (:524-546)
+        for (int h = hf_offset[c]; h < hf_offset[c + 1]; ++h) {
+            const int c1 = hf_neighbour[h];
+            if (c1 >= 0) {
+                if (c1 >= n_cells || c1 == c) return EU_ERR_ARG;
+                if (c1 > c) faces.push_back(c1);          // neighbour not visited yet: a new interior face
+            }
+        }
+        fpos[size_t(c) + 1] = int(faces.size());
+        max_ncf = std::max(max_ncf, hf_offset[c + 1] - hf_offset[c]);
+    }
+    int total = int(faces.size());
+    for (int c = 0; c < n_cells; ++c) {           // second pass (:566-599)
+        for (int h = hf_offset[c]; h < hf_offset[c + 1]; ++h) {
+            const int c1 = hf_neighbour[h];
+            if (c1 < 0) { face_index[h] = total++; continue; }
+            const int t = std::min(c, c1), seek = std::max(c, c1);
+            const int* b = faces.data() + fpos[size_t(t)];
+            const int* e = faces.data() + fpos[size_t(t) + 1];
+            const int* p = std::find(b, e, seek);
+            if (p == e) return EU_ERR_ARG;                 // adjacency not symmetric
+            face_index[h] = int(p - faces.data());
+        }
+    }
+    if (num_faces) *num_faces = total;
+    if (max_faces_per_cell) *max_faces_per_cell = max_ncf;
+    return EU_OK;
+}
+
+// IncompFlowSolverHybrid::postProcessFluxes (mimetic/IncompFlowSolverHybrid.hpp:707-807): the out-fluxes of the two
+// half-faces of a face are made exactly antisymmetric, f -> +-0.5 (f_first - f_second) in walk order; boundary faces
+// are left alone unless they have a periodic partner (partner_face[face] >= 0; NULL = no periodic faces, :770-772),
+// in which case the pair is treated like the two sides of one face.  Same accumulation order as FaceFluxes::put / get.
+// Returns the largest modification in *max_modification.  This is the step that produces the hf_flux array handed to
+// eu_transport_solve.
+int eu_post_process_fluxes(int n_cells, const int* hf_offset, const int* hf_neighbour, const int* face_index, int num_faces,
+                           const int* partner_face, double* hf_flux, double* max_modification)
+{
+    if (n_cells < 0 || !hf_offset || !hf_neighbour || !face_index || !hf_flux || num_faces < 0) return EU_ERR_ARG;
+    std::vector<double> fluxes(size_t(num_faces), 0.0);
+    std::vector<unsigned char> visited(size_t(num_faces), 0);
+    double max_mod = 0.0;
+    auto put = [&](double flux, int f) {
+        fluxes[size_t(f)] += (visited[size_t(f)] ? -1.0 : 1.0)*flux;
+        ++visited[size_t(f)];
+    };
+    auto get = [&](double& flux, int f) {
+        const double nf = 0.5*(visited[size_t(f)] ? -1.0 : 1.0)*fluxes[size_t(f)];
+        max_mod = std::max(max_mod, std::fabs(flux - nf));
+        flux = nf;
+        ++visited[size_t(f)];
+    };
+    const long long H = hf_offset[n_cells];
+    for (long long h = 0; h < H; ++h) {
+        const int f = face_index[h];
+        if (f < 0 || f >= num_faces) return EU_ERR_ARG;
+        if (hf_neighbour[h] < 0) {
+            if (!partner_face) continue;
+            const int pf = partner_face[f];
+            if (pf != -1) { put(hf_flux[h], f); put(hf_flux[h], pf); }
+        } else {
+            put(hf_flux[h], f);
+        }
+    }
+    std::fill(visited.begin(), visited.end(), 0);
+    for (long long h = 0; h < H; ++h) {
+        const int f = face_index[h];
+        if (hf_neighbour[h] < 0) {
+            if (!partner_face) continue;
+            const int pf = partner_face[f];
+            if (pf != -1) {
+                get(hf_flux[h], f);
+                double dummy = hf_flux[h];
+                get(dummy, pf);
+            }
+        } else {
+            get(hf_flux[h], f);
+        }
+    }
+    if (max_modification) *max_modification = max_mod;
+    return EU_OK;
+}
+
+// writeField (common/SimulatorUtilities.hpp:288-298): the saturation file the drivers write after every step
+// (SimulatorBase / SimulatorTester: "<prefix>-<step>.sat"): the size, then one value per line in the stream's default
+// formatting.  Returns EU_ERR_ARG when the file cannot be opened (the reference throws).
+int eu_write_field(const double* field, long long n, const char* filename)
+{
+    if (!field || n < 0 || !filename) return EU_ERR_ARG;
+    std::ofstream os(filename);
+    if (!os) return EU_ERR_ARG;
+    os << (unsigned long)n << '\n';
+    std::copy(field, field + n, std::ostream_iterator<double>(os, "\n"));
+    return os ? EU_OK : EU_ERR_ARG;
+}
+
+} // extern "C"

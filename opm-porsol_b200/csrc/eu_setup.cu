@@ -2,6 +2,7 @@
 // Compile with -fmad=false: everything numeric here follows the reference's operation order
 // (see eu_strict_math.cuh) and is bit-identical to it.
 #include "eu_internal.h"
+#include <algorithm>
 
 #include <climits>
 #include "eu_strict_math.cuh"
@@ -522,10 +523,15 @@ __device__ __forceinline__ void block_min_store(double v, double* __restrict__ b
     }
 }
 
+// min over n block minima: a grid of up to kFinalBlocks blocks writes one partial minimum each behind the inputs
+// (block_min has room for them, eu_cfl_blocks), a last block reduces those.  (One block over all the minima of a 67 M-cell
+// grid was a chain of a thousand dependent loads per thread: 60 us per CFL term.)  The minimum is exact in any order.
+constexpr int kFinalBlocks = 256;
 __global__ void k_final_min(const double* __restrict__ block_min, int n, double* __restrict__ out)
 {
     double v = 1e100;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) v = min_keep(v, block_min[i]);
+    for (int i = blockIdx.x*blockDim.x + threadIdx.x; i < n; i += gridDim.x*blockDim.x) v = min_keep(v, block_min[i]);
+    out += blockIdx.x;
     __shared__ double sm[kThreads/32];
     for (int o = 16; o > 0; o >>= 1) v = min_keep(v, __shfl_xor_sync(0xffffffffu, v, o));
     if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
@@ -941,27 +947,36 @@ void eu_launch_pcscale(const EuGridDev& g, const EuTablesDev& t, double* pcscale
 {
     k_pcscale<<<div_up(g.n_local, kThreads), kThreads, 0, st>>>(g, t, pcscale, rock8, inv_porevol);
 }
-int eu_cfl_blocks(int n_cells) { return div_up(n_cells > 0 ? n_cells : 1, kThreads); }
+// blocks of the CFL kernels = block minima, plus room for the partial minima of the final reduction
+int eu_cfl_blocks(int n_cells) { return div_up(n_cells > 0 ? n_cells : 1, kThreads) + kFinalBlocks; }
+static int cfl_grid(int n_cells) { return div_up(n_cells > 0 ? n_cells : 1, kThreads); }
+static void launch_final_min(double* block_min, int nb, double* out, cudaStream_t st)
+{
+    const int parts = std::min(kFinalBlocks, div_up(nb, kThreads));
+    if (parts <= 1) { k_final_min<<<1, kThreads, 0, st>>>(block_min, nb, out); return; }
+    k_final_min<<<parts, kThreads, 0, st>>>(block_min, nb, block_min + nb);
+    k_final_min<<<1, kThreads, 0, st>>>(block_min + nb, parts, out);
+}
 
 void eu_launch_cfl_velocity_compact(const EuGridDev& g, double cfl_factor, const double* hf_flux, const int* fid_of_hf,
                                     double* q, double* block_min, int* zero_flag, double* out, cudaStream_t st)
 {
-    const int nb = eu_cfl_blocks(g.n_local);
+    const int nb = cfl_grid(g.n_local);
     k_cfl_velocity_compact<<<nb, kThreads, 0, st>>>(g, cfl_factor, hf_flux, fid_of_hf, q, block_min, zero_flag);
-    k_final_min<<<1, kThreads, 0, st>>>(block_min, nb, out);
+    launch_final_min(block_min, nb, out, st);
 }
 void eu_launch_cfl_gravity(const EuGridDev& g, const EuTablesDev& t, double cfl_factor, const double gravity[3],
                            double* block_min, double* out, cudaStream_t st)
 {
-    const int nb = eu_cfl_blocks(g.own_hi - g.own_lo);
+    const int nb = cfl_grid(g.own_hi - g.own_lo);
     k_cfl_gravity<<<nb, kThreads, 0, st>>>(g, t, cfl_factor, gravity[0], gravity[1], gravity[2], block_min);
-    k_final_min<<<1, kThreads, 0, st>>>(block_min, nb, out);
+    launch_final_min(block_min, nb, out, st);
 }
 void eu_launch_cfl_capillary(const EuGridDev& g, double cfl_factor, double* block_min, double* out, cudaStream_t st)
 {
-    const int nb = eu_cfl_blocks(g.own_hi - g.own_lo);
+    const int nb = cfl_grid(g.own_hi - g.own_lo);
     k_cfl_capillary<<<nb, kThreads, 0, st>>>(g, cfl_factor, block_min);
-    k_final_min<<<1, kThreads, 0, st>>>(block_min, nb, out);
+    launch_final_min(block_min, nb, out, st);
 }
 void eu_launch_strict_pc(const EuGridDev& g, const EuTablesDev& t, const double* S, double* pc, cudaStream_t st)
 {

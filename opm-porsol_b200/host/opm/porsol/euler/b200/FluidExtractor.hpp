@@ -110,6 +110,12 @@ namespace b200 {
                 const Tab& krw = rocks[r].*get(JKrw());
                 const Tab& kro = rocks[r].*get(JKro());
                 const Tab& J = rocks[r].*get(JJ());
+                // one saturation column per rock in the C ABI: the three curves must share their nodes (they do when read
+                // from the reference's rock files, RockJfunc.hpp:196-228, one row per saturation)
+                if (xs(kro) != xs(krw) || xs(J) != xs(krw))
+                    throw std::runtime_error("rock table: krw, kro and J must share their saturation nodes");
+                if (ys(krw).size() != xs(krw).size() || ys(kro).size() != xs(krw).size() || ys(J).size() != xs(krw).size())
+                    throw std::runtime_error("rock table: columns of different lengths");
                 fd.table_s.insert(fd.table_s.end(), xs(krw).begin(), xs(krw).end());
                 fd.cols[0].insert(fd.cols[0].end(), ys(krw).begin(), ys(krw).end());
                 fd.cols[1].insert(fd.cols[1].end(), ys(kro).begin(), ys(kro).end());
@@ -142,7 +148,8 @@ namespace b200 {
                     const Tab& kx = (rocks[r].*get(AKx()))[ph];
                     const Tab& ky = (rocks[r].*get(AKy()))[ph];
                     const Tab& kz = (rocks[r].*get(AKz()))[ph];
-                    if (xs(kx) != xs(pc)) throw std::runtime_error("anisotropic rock: phase tables must share saturation nodes");
+                    if (xs(kx) != xs(pc) || xs(ky) != xs(pc) || xs(kz) != xs(pc))
+                        throw std::runtime_error("anisotropic rock: phase tables must share saturation nodes");
                     fd.cols[1 + 3*ph].insert(fd.cols[1 + 3*ph].end(), ys(kx).begin(), ys(kx).end());
                     fd.cols[2 + 3*ph].insert(fd.cols[2 + 3*ph].end(), ys(ky).begin(), ys(ky).end());
                     fd.cols[3 + 3*ph].insert(fd.cols[3 + 3*ph].end(), ys(kz).begin(), ys(kz).end());

@@ -216,6 +216,13 @@ def ref_find_periodic_partners(centroid, area, is_periodic, spatial_tolerance=1e
     return st, canon[:n], partner[:n], sides
 
 
+def ref_write_field(field, filename):
+    """The reference's writeField (SimulatorUtilities.hpp:288-298)."""
+    lib = C.CDLL(REF_LIB)
+    f = np.ascontiguousarray(field, dtype=np.float64)
+    return lib.ref_write_field(_d(f), C.c_int(f.shape[0]), C.c_char_p(filename.encode()))
+
+
 # ------------------------------------------------------------------------------------
 # plain-C restatement
 # ------------------------------------------------------------------------------------

@@ -534,4 +534,15 @@ void ref_mobility(void* hv, int phase, int cell, double s, double* out9) { stati
 double ref_frac_flow(void* hv, int cell, double s) { return static_cast<HarnessBase*>(hv)->fracFlow(cell, s); }
 const char* ref_last_error(void* hv) { return static_cast<HarnessBase*>(hv)->last_error.c_str(); }
 
+// writeField (SimulatorUtilities.hpp:288-298): returns 1 if the reference threw
+int ref_write_field(const double* field, int n, const char* filename)
+{
+    try {
+        Opm::writeField(std::vector<double>(field, field + n), filename);
+    } catch (...) {
+        return 1;
+    }
+    return 0;
+}
+
 } // extern "C"
