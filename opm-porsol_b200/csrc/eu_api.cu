@@ -117,6 +117,7 @@ struct eu_solver {
     DevBuf<double> d_porevol, d_inv_porevol, d_pcscale, d_T, d_nn;
     DevBuf<double2> d_lam[2];          // per cell {lambda_w, lambda_o} of the state in d_S[k] (FAST)
     DevBuf<double2> d_qg;              // per unique face {flux of the current transportSolve, G}
+    DevBuf<double> d_qa, d_Ga;         // the axis planes' q and G as separate arrays [3][n_local] (box kernel: G only where needed)
     DevBuf<unsigned char> d_rock8;
     long long F = 0;
     int axis[3] = { 0, 0, 0 };         // neighbour offsets of the axis planes of the face arrays (0 = none)
@@ -345,17 +346,20 @@ int ensure_contracted(eu_handle h, const double gravity[3])
     if (h->contracted && h->contracted_mg == mg && std::memcmp(h->contracted_gravity, gravity, 3*sizeof(double)) == 0)
         return EU_OK;
     eu_launch_contract(h->grid(), h->tab, h->d_owner_hf.p, h->d_fid_of_hf.p, gravity, mg, reinterpret_cast<double*>(h->d_qg.p) + 1, h->d_T.p, h->d_nn.p,
-                       h->d_scalars.p + 8, h->st);
+                       h->d_scalars.p + 8, h->d_Ga.p, h->d_Ga.p ? h->d_flags.p + 2 : nullptr, h->st);
     double maxdev = 0.0;
+    int gmask = 7;
     EU_CUDA(h, cudaMemcpyAsync(&maxdev, h->d_scalars.p + 8, sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    if (h->d_Ga.p) EU_CUDA(h, cudaMemcpyAsync(&gmask, h->d_flags.p + 2, sizeof(int), cudaMemcpyDeviceToHost, h->st));
     EU_CUDA(h, cudaStreamSynchronize(h->st));
+    eu_box_plan_set_gravity_mask(h->box, gmask);
     EU_CUDA(h, cudaGetLastError());
     h->use_nn = maxdev > 1e-13;     // non-unit normals: keep the n.n factor of the viscous term
     if (h->use_nn && h->d_nn.n == 0) {
         EU_CUDA(h, h->d_nn.alloc(size_t(std::max<long long>(h->F, 1)) + 1));
         EU_CUDA(h, cudaMemsetAsync(h->d_nn.p, 0, h->d_nn.n*sizeof(double), h->st));
         eu_launch_contract(h->grid(), h->tab, h->d_owner_hf.p, h->d_fid_of_hf.p, gravity, mg, reinterpret_cast<double*>(h->d_qg.p) + 1, h->d_T.p, h->d_nn.p,
-                           h->d_scalars.p + 8, h->st);
+                           h->d_scalars.p + 8, nullptr, nullptr, h->st);
         EU_CUDA(h, cudaStreamSynchronize(h->st));
     }
     if (h->tensor_fast == 2)
@@ -817,7 +821,7 @@ int compute_cfl(eu_handle h, const double gravity[3], bool want_v, bool want_g, 
     // The velocity pass also compacts the half-face fluxes for the FAST kernel, so it always runs.
     EU_CUDA(h, cudaMemsetAsync(h->d_flags.p, 0, 4*sizeof(int), h->st));
     eu_launch_cfl_velocity_compact(g, h->fluid.cfl_factor[0], h->d_hf_flux.p, h->d_fid_of_hf.p,
-                                   h->mode == EU_MODE_FAST ? reinterpret_cast<double*>(h->d_qg.p) : nullptr, h->d_block_min.p, h->d_flags.p,
+                                   h->mode == EU_MODE_FAST ? reinterpret_cast<double*>(h->d_qg.p) : nullptr, h->d_qa.p, h->d_block_min.p, h->d_flags.p,
                                    h->d_scalars.p + 0, h->st);
     *launches += 2;
     const bool grav_cached = h->cfl_grav_valid && std::memcmp(h->cfl_grav_gravity, gravity, 3*sizeof(double)) == 0;
@@ -957,6 +961,8 @@ int eu_grid_begin(eu_handle h, int n_cells_global, int n_local_cells, long long 
     h->grid_open = true; h->grid_ready = false; h->state_ready = false; h->contracted = false;
     eu_box_plan_destroy(h->box);
     h->box = nullptr;
+    h->d_qa.release();
+    h->d_Ga.release();
     h->cfl_cap_valid = h->cfl_grav_valid = false;
     h->n_global = n_cells_global; h->n_local_expected = n_local_cells; h->H_expected = n_local_halffaces;
     h->n_local = 0; h->H = 0;
@@ -1379,8 +1385,12 @@ int eu_grid_end(eu_handle h)
         EU_CUDA(h, cudaMemcpyAsync(&n_irr, h->d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, h->st));
         EU_CUDA(h, cudaStreamSynchronize(h->st));
         const int nx = h->axis[1], ny = h->axis[2]/h->axis[1], nz = h->n_local/h->axis[2];
+        EU_CUDA(h, h->d_qa.alloc(3*n));
+        EU_CUDA(h, h->d_Ga.alloc(3*n));
+        EU_CUDA(h, cudaMemsetAsync(h->d_qa.p, 0, 3*n*sizeof(double), h->st));
+        EU_CUDA(h, cudaMemsetAsync(h->d_Ga.p, 0, 3*n*sizeof(double), h->st));
         h->box = eu_box_plan_create(nx, ny, nz, h->own_lo/h->axis[2], h->own_hi/h->axis[2], h->d_S[0].p, h->d_S[1].p, h->d_pc[0].p,
-                                    h->d_pc[1].p, h->d_qg.p, h->d_T.p, h->d_cmask.p, h->d_irr_cells.p, n_irr, h->d_acc_irr.p, h->n_sms);
+                                    h->d_pc[1].p, h->d_qa.p, h->d_Ga.p, h->d_T.p, h->d_cmask.p, h->d_irr_cells.p, n_irr, h->d_acc_irr.p, h->n_sms);
     }
     EU_CUDA(h, cudaStreamSynchronize(h->st));
     EU_CUDA(h, cudaGetLastError());

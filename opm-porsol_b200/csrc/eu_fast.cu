@@ -929,11 +929,13 @@ __global__ void __launch_bounds__(kBlock) k_fast_state(EuGridDev g, EuTablesDev 
 struct EuBoxPlan {
     int nx = 0, ny = 0, nz = 0, z_lo = 0, z_hi = 0, n_local = 0;
     int tx = 0, ty = 0, threads = 0;
-    CUtensorMap mapS[2], mapPc[2], mapQG, mapT;
+    CUtensorMap mapS[2], mapPc[2], mapQ, mapG, mapT;
+    int g_mask = 7;                                  // axis planes with a gravity component (set after the contraction)
     int4* d_units = nullptr;
     int n_units = 0, n_bnd_units[2] = { 0, 0 }, n_flagged = 0;
     int units_key[5] = { -1, -1, -1, -1, -1 };      // (bnd planes lo, hi, grid blocks, lz override, cap) the unit list was built for
     const unsigned short* cmask = nullptr;
+    int g_mask_seen = -1;
     size_t smem_set[32] = { 0 };
     int blocks_per_sm[32] = { 0 };
     const int* irr_cells = nullptr;
@@ -987,14 +989,16 @@ BoxLayout box_layout(const EuBoxPlan& p, bool cap, bool multirock, int stages, s
     const int cells = (p.tx + 2)*(p.ty + 2);
     b.lam_bytes = cap ? 2*r128(cells*16) : r128(cells*16);      // {lw, lo} entries, then (capillary) {S, pc} entries
     b.rk_bytes = (cap && multirock) ? r128(cells) : 0;
-    b.qg_bytes = r128((p.tx + 1)*(p.ty + 1)*16);
-    b.T_bytes = cap ? r128((p.tx + 2)*(p.ty + 1)*8) : 0;
+    b.T_bytes = r128((p.tx + 2)*(p.ty + 1)*8);               // one box of q, G or T
+    b.g_mask = p.g_mask & 7;
+    const int n_G = ((b.g_mask >> 0) & 1) + ((b.g_mask >> 1) & 1) + ((b.g_mask >> 2) & 1);
     const int S_bytes = r128((p.tx + 4)*(p.ty + 2)*8);
     b.off_S = 0;
     b.off_pc = S_bytes;
-    b.off_qg = S_bytes*(cap ? 2 : 1);
-    b.off_T = b.off_qg + 3*b.qg_bytes;
-    b.stage_bytes = b.off_T + 3*b.T_bytes;
+    b.off_q = S_bytes*(cap ? 2 : 1);
+    b.off_G = b.off_q + 3*b.T_bytes;
+    b.off_T = b.off_G + n_G*b.T_bytes;
+    b.stage_bytes = b.off_T + (cap ? 3*b.T_bytes : 0);
     b.off_bar = 0;
     b.off_lam = 128;
     b.off_rk = b.off_lam + 3*b.lam_bytes;
@@ -1018,7 +1022,7 @@ void eu_box_plan_destroy(EuBoxPlan* p)
 
 // nullptr when the box kernel does not apply (then the slice-class kernel runs)
 EuBoxPlan* eu_box_plan_create(int nx, int ny, int nz, int z_lo, int z_hi, double* S0, double* S1, double* pc0, double* pc1,
-                              double2* qg, double* T, const unsigned short* cmask, const int* irr_cells, int n_irr, double* acc_irr, int n_sms)
+                              double* qa, double* Ga, double* T, const unsigned short* cmask, const int* irr_cells, int n_irr, double* acc_irr, int n_sms)
 {
     // TMA: global strides are multiples of 16 bytes (nx even); coordinates fit the unit encoding
     if (nx < 2 || (nx & 1) || ny < 1 || nz < 1 || nx > 65535 || ny > 32767) return nullptr;
@@ -1060,20 +1064,17 @@ EuBoxPlan* eu_box_plan_create(int nx, int ny, int nz, int z_lo, int z_hi, double
         ok = ok && make_map(&p->mapPc[0], pc0, 3, dims, str, box) && make_map(&p->mapPc[1], pc1, 3, dims, str, box);
     }
     {
-        cuuint64_t dims[4] = { cuuint64_t(2*nx), cuuint64_t(ny), cuuint64_t(nz), 3 };
-        cuuint64_t str[3] = { cuuint64_t(nx)*16, cuuint64_t(nx)*ny*16, n*16 };
-        cuuint32_t box[4] = { cuuint32_t(2*(p->tx + 1)), cuuint32_t(p->ty + 1), 1, 1 };
-        ok = ok && make_map(&p->mapQG, qg, 4, dims, str, box);
-    }
-    {
+        // the three axis planes of q, G and T: [3][nz][ny][nx] doubles, boxes of (tx+2) x (ty+1) (x boxes start at x0 - 2)
         cuuint64_t dims[4] = { cuuint64_t(nx), cuuint64_t(ny), cuuint64_t(nz), 3 };
         cuuint64_t str[3] = { cuuint64_t(nx)*8, cuuint64_t(nx)*ny*8, n*8 };
         cuuint32_t box[4] = { cuuint32_t(p->tx + 2), cuuint32_t(p->ty + 1), 1, 1 };
-        ok = ok && make_map(&p->mapT, T, 4, dims, str, box);
+        ok = ok && make_map(&p->mapQ, qa, 4, dims, str, box) && make_map(&p->mapG, Ga, 4, dims, str, box) && make_map(&p->mapT, T, 4, dims, str, box);
     }
     if (!ok) { eu_box_plan_destroy(p); return nullptr; }
     return p;
 }
+
+void eu_box_plan_set_gravity_mask(EuBoxPlan* p, int mask) { if (p) p->g_mask = mask & 7; }
 
 void eu_box_plan_info(const EuBoxPlan* p, int out[6])
 {
@@ -1185,6 +1186,7 @@ static int launch_box(EuBoxPlan* p, const EuGridDev& g, const EuTablesDev& t, co
     // function attributes are per device: a plan remembers what it set on ITS device (several solvers, one per GPU, may
     // live in one process)
     const int vkey = (share ? 16 : 0) + (minb_env == 4 ? 8 : 0) + (two ? 4 : 0) + stages - 2;
+    if (p->g_mask_seen != p->g_mask) { std::memset(p->smem_set, 0, sizeof(p->smem_set)); std::memset(p->blocks_per_sm, 0, sizeof(p->blocks_per_sm)); p->g_mask_seen = p->g_mask; p->units_key[0] = -1; }
     if (lay.total > p->smem_set[vkey]) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total) != cudaSuccess) return -1;
         p->smem_set[vkey] = lay.total;
@@ -1213,7 +1215,7 @@ static int launch_box(EuBoxPlan* p, const EuGridDev& g, const EuTablesDev& t, co
         ++launches;
     }
     const int blocks = std::min(grid_full, p->n_units);
-    kern<<<blocks, p->threads, lay.total, st>>>(p->mapS[cur], p->mapPc[cur], p->mapQG, p->mapT, g, t, f, a, halo, lay.b, slice_lo, slice_hi, (int)tab_bytes);
+    kern<<<blocks, p->threads, lay.total, st>>>(p->mapS[cur], p->mapPc[cur], p->mapQ, p->mapG, p->mapT, g, t, f, a, halo, lay.b, slice_lo, slice_hi, (int)tab_bytes);
     return launches;
 }
 

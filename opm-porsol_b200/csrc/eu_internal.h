@@ -189,9 +189,11 @@ void eu_launch_cell_mask(const EuGridDev& g, const int* slice_base, const int2* 
                          cudaStream_t st);
 void eu_launch_build_records(const EuGridDev& g, const int* owner_hf, const int* fid_of_hf, const unsigned char* slot_of_hf,
                              const int* slice_base, int2* rec, int2* desc, int* n_regular_slots, cudaStream_t st);
+// Ga (3*n_local doubles, may be NULL): G of the faces in the axis planes as a separate array (box kernel);
+// gmask_out (device int, may be NULL): bit a set when axis plane a has a non-zero G
 void eu_launch_contract(const EuGridDev& g, const EuTablesDev& t, const int* owner_hf, const int* fid_of_hf,
                         const double gravity[3], int method_gravity, double* G, double* T, double* nn,
-                        double* nn_maxdev, cudaStream_t st);
+                        double* nn_maxdev, double* Ga, int* gmask_out, cudaStream_t st);
 // tensor mobility in FAST mode: are all face normals axis-aligned (flag[0] |= 1 if not)?  axis per unique face
 void eu_launch_contract_t3(const EuGridDev& g, const EuTablesDev& t, const int* owner_hf, const int* fid_of_hf,
                            const double gravity[3], int method_gravity, double* fv, long long stride, cudaStream_t st);
@@ -199,8 +201,9 @@ void eu_launch_axis_check(const EuGridDev& g, int* flag, cudaStream_t st);
 void eu_launch_face_axis(const EuGridDev& g, const int* owner_hf, const int* fid_of_hf, unsigned char* axis8, cudaStream_t st);
 void eu_launch_pcscale(const EuGridDev& g, const EuTablesDev& t, double* pcscale, unsigned char* rock8, double* inv_porevol, cudaStream_t st);
 // CFL terms (CflCalculator.hpp); results are block minima reduced to out[0]
+// qa (3*n_local doubles, may be NULL): the flux of the faces in the axis planes as a separate array (box kernel)
 void eu_launch_cfl_velocity_compact(const EuGridDev& g, double cfl_factor, const double* hf_flux, const int* fid_of_hf,
-                                    double* q, double* block_min, int* zero_flag, double* out, cudaStream_t st);
+                                    double* q, double* qa, double* block_min, int* zero_flag, double* out, cudaStream_t st);
 void eu_launch_cfl_gravity(const EuGridDev& g, const EuTablesDev& t, double cfl_factor, const double gravity[3],
                            double* block_min, double* out, cudaStream_t st);
 void eu_launch_cfl_capillary(const EuGridDev& g, double cfl_factor, double* block_min, double* out, cudaStream_t st);
@@ -232,8 +235,9 @@ size_t eu_fast_smem_bytes(const EuTablesDev& t);
 // box kernel (eu_tile.cuh): plane sweep over tiles with TMA-staged operands, for local numberings that are a box
 struct EuBoxPlan;
 EuBoxPlan* eu_box_plan_create(int nx, int ny, int nz, int z_lo, int z_hi, double* S0, double* S1, double* pc0, double* pc1,
-                              double2* qg, double* T, const unsigned short* cmask, const int* irr_cells, int n_irr, double* acc_irr, int n_sms);
+                              double* qa, double* Ga, double* T, const unsigned short* cmask, const int* irr_cells, int n_irr, double* acc_irr, int n_sms);
 void eu_box_plan_destroy(EuBoxPlan* p);
+void eu_box_plan_set_gravity_mask(EuBoxPlan* p, int mask);    // bit a: axis plane a has a non-zero G somewhere
 void eu_box_plan_info(const EuBoxPlan* p, int out[6]);      // tile x, tile y, units, boundary units A, B, threads per block
 // builds (or reuses) the work units for `bnd_lo` / `bnd_hi` boundary planes at the two ends of the own range; info as above
 int eu_box_plan_units(EuBoxPlan* p, int bnd_lo, int bnd_hi, bool capillary, int info[6]);

@@ -370,7 +370,7 @@ __global__ void k_build_records(EuGridDev g, const int* __restrict__ owner_hf, c
 __global__ void k_contract(EuGridDev g, EuTablesDev t, const int* __restrict__ owner_hf,
                            const int* __restrict__ fid_of_hf, double gx, double gy, double gz, int method_gravity,
                            double* __restrict__ G, double* __restrict__ T, double* __restrict__ nn,
-                           unsigned long long* __restrict__ nn_maxdev_bits)
+                           unsigned long long* __restrict__ nn_maxdev_bits, double* __restrict__ Ga, int* __restrict__ gmask)
 {
     int c = blockIdx.x*blockDim.x + threadIdx.x;
     if (c >= g.n_local) return;
@@ -397,7 +397,12 @@ __global__ void k_contract(EuGridDev g, EuTablesDev t, const int* __restrict__ o
         for (int i = 0; i < 3; ++i) gi[i] *= t.delta_rho;
         const double area = g.hf_area[h];
         const double nrm[3] = { g.hf_normal[3LL*h], g.hf_normal[3LL*h + 1], g.hf_normal[3LL*h + 2] };
-        G[2LL*fid] = method_gravity ? area*sm_inner3(nrm, gi) : 0.0;       // interleaved {q, G} pairs
+        const double Gv = method_gravity ? area*sm_inner3(nrm, gi) : 0.0;
+        G[2LL*fid] = Gv;                                                   // interleaved {q, G} pairs
+        if (Ga && fid < 3*g.n_local) {                                     // axis planes: also as a separate array
+            Ga[fid] = Gv;
+            if (Gv != 0.0 && gmask) atomicOr(gmask, 1 << (fid/g.n_local));
+        }
         double Tv = 0.0;
         if (interior_like) {
             double dirhat[3], d0d1, ci[3];
@@ -546,7 +551,7 @@ __global__ void k_final_min(const double* __restrict__ block_min, int n, double*
 // euler/CflCalculator.hpp:54-83 fused with the per-call compaction of the half-face fluxes to
 // one value per unique face (the owner's outflux, euler/EulerUpstreamResidual_impl.hpp:147)
 __global__ void k_cfl_velocity_compact(EuGridDev g, double cfl_factor, const double* __restrict__ hf_flux,
-                                       const int* __restrict__ fid_of_hf, double* __restrict__ q,
+                                       const int* __restrict__ fid_of_hf, double* __restrict__ q, double* __restrict__ qa,
                                        double* __restrict__ block_min, int* __restrict__ zero_flag)
 {
     int c = blockIdx.x*blockDim.x + threadIdx.x;
@@ -557,7 +562,13 @@ __global__ void k_cfl_velocity_compact(EuGridDev g, double cfl_factor, const dou
         for (int h = b; h < e; ++h) {
             const double f = hf_flux[h];
             if (f > 0) flux_p += f; else flux_n -= f;
-            if (q) { const int fid = fid_of_hf[h]; if (fid >= 0) q[2LL*fid] = f; }      // interleaved {q, G} pairs
+            if (q) {
+                const int fid = fid_of_hf[h];
+                if (fid >= 0) {
+                    q[2LL*fid] = f;                                        // interleaved {q, G} pairs
+                    if (qa && fid < 3*g.n_local) qa[fid] = f;              // axis planes: also as a separate array (box kernel)
+                }
+            }
         }
         if (c >= g.own_lo && c < g.own_hi) {
             const double flux = flux_n > flux_p ? flux_n : flux_p;         // std::max(flux_n, flux_p)
@@ -922,11 +933,12 @@ void eu_launch_build_records(const EuGridDev& g, const int* owner_hf, const int*
 }
 void eu_launch_contract(const EuGridDev& g, const EuTablesDev& t, const int* owner_hf, const int* fid_of_hf,
                         const double gravity[3], int method_gravity, double* G, double* T, double* nn,
-                        double* nn_maxdev, cudaStream_t st)
+                        double* nn_maxdev, double* Ga, int* gmask_out, cudaStream_t st)
 {
     cudaMemsetAsync(nn_maxdev, 0, sizeof(double), st);
+    if (gmask_out) cudaMemsetAsync(gmask_out, 0, sizeof(int), st);
     k_contract<<<div_up(g.n_local, kThreads), kThreads, 0, st>>>(g, t, owner_hf, fid_of_hf, gravity[0], gravity[1], gravity[2],
-                                                                 method_gravity, G, T, nn, (unsigned long long*)nn_maxdev);
+                                                                 method_gravity, G, T, nn, (unsigned long long*)nn_maxdev, Ga, gmask_out);
 }
 void eu_launch_contract_t3(const EuGridDev& g, const EuTablesDev& t, const int* owner_hf, const int* fid_of_hf,
                            const double gravity[3], int method_gravity, double* fv, long long stride, cudaStream_t st)
@@ -959,10 +971,10 @@ static void launch_final_min(double* block_min, int nb, double* out, cudaStream_
 }
 
 void eu_launch_cfl_velocity_compact(const EuGridDev& g, double cfl_factor, const double* hf_flux, const int* fid_of_hf,
-                                    double* q, double* block_min, int* zero_flag, double* out, cudaStream_t st)
+                                    double* q, double* qa, double* block_min, int* zero_flag, double* out, cudaStream_t st)
 {
     const int nb = cfl_grid(g.n_local);
-    k_cfl_velocity_compact<<<nb, kThreads, 0, st>>>(g, cfl_factor, hf_flux, fid_of_hf, q, block_min, zero_flag);
+    k_cfl_velocity_compact<<<nb, kThreads, 0, st>>>(g, cfl_factor, hf_flux, fid_of_hf, q, qa, block_min, zero_flag);
     launch_final_min(block_min, nb, out, st);
 }
 void eu_launch_cfl_gravity(const EuGridDev& g, const EuTablesDev& t, double cfl_factor, const double gravity[3],

@@ -11,7 +11,7 @@
 // Per plane k one bundle of operands arrives in shared memory by TMA (cp.async.bulk.tensor, mbarrier completion),
 // two or three planes ahead of its use:
 //     S(k+1)  [and pc(k+1)]   the tile plus a halo (2 cells in x, 1 in y)         3-D box  (tx+4) x (ty+2) x 1
-//     {q, G}(k) of the x-, y- and z-faces [and T(k)]                              4-D boxes (tx+1) x (ty+1) x 1 x 1
+//     q(k) of the x-, y- and z-faces, G(k) of the axes that have gravity [, T(k)]  4-D boxes (tx+2) x (ty+1) x 1 x 1
 // (a box of 8-byte elements must start at an even innermost coordinate -- 16 bytes; an odd one raises an illegal-
 // instruction fault, tools/probe/tma_probe.cu -- hence the second halo column in x, which is never read)
 // Out-of-range coordinates (halo outside the grid, plane -1 or nz) are zero-filled by the TMA unit: a zero face carries no
@@ -36,9 +36,10 @@ struct EuBoxDev {
     int stages;                   // bundles in flight
     int off_bar, off_lam, off_rk, off_stage;      // byte offsets in dynamic shared memory (from the 128-aligned base)
     int lam_bytes, rk_bytes, stage_bytes;
-    int off_S, off_pc, off_qg, off_T;             // inside a stage
+    int off_S, off_pc, off_q, off_G, off_T;       // inside a stage
+    int g_mask;                                   // bit a: the faces of axis plane a have a gravity component somewhere (G box loaded)
     int off_fx, off_fy, fx_bytes, fy_bytes;       // SHARE: two buffers each of x+ fluxes [ty][tx+1] and y+ fluxes [ty+1][tx]
-    int qg_bytes, T_bytes;                        // one axis' box
+    int T_bytes;                                  // one axis' box of q, G or T
     int n_flagged;                // units with a push flag (they are the first of the list)
     const unsigned short* cmask;  // per cell: record slots with faces outside the axis planes
     const double* acc_irr;        // per cell with a non-zero mask: sum of those faces' contributions (k_box_irregular)
@@ -91,19 +92,20 @@ __device__ __forceinline__ double face_no_gravity(double q, double lw0, double l
     return dS;
 }
 
-// one regular face of the box kernel (method_viscous is on: the host sends other runs to the slice-class kernel)
+// one regular face of the box kernel (method_viscous is on: the host sends other runs to the slice-class kernel).
+// has_G: the face's axis plane has a gravity component somewhere (uniform over the launch); without it -- every lateral
+// face of a horizontally layered grid -- no G is loaded at all and both phases are upwinded by the sign of q.
 template <bool ROCKS, bool MULTIROCK, bool CAP, bool OWN>
 __device__ __forceinline__ double box_face(const TabLayout& L, const EuTablesDev& t, const MarchCarry& m, double lw1, double lo1,
-                                           double S1, double pc1, int rk1, double2 qg, double T)
+                                           double S1, double pc1, int rk1, double q, double G, bool has_G, double T)
 {
     double cap_coef = 0.0, Tdpc = 0.0;
     if (CAP) {
         cap_coef = cap_coefficient<ROCKS, MULTIROCK>(L, t, m.rock0, rk1, m.S0, S1);
         Tdpc = T*(OWN ? (pc1 - m.pc0) : (m.pc0 - pc1));
     }
-    if (__all_sync(__activemask(), qg.y == 0.0))           // warp-uniform
-        return face_no_gravity<OWN, CAP>(qg.x, m.lw0, m.lo0, lw1, lo1, cap_coef, Tdpc);
-    return face_regular<OWN, CAP>(qg.x, qg.x, qg.y, m.lw0, m.lo0, lw1, lo1, 1, cap_coef, Tdpc);
+    if (!has_G) return face_no_gravity<OWN, CAP>(q, m.lw0, m.lo0, lw1, lo1, cap_coef, Tdpc);
+    return face_regular<OWN, CAP>(q, q, G, m.lw0, m.lo0, lw1, lo1, 1, cap_coef, Tdpc);
 }
 
 // the faces of a cell outside the axis planes (boundary, fault, periodic wrap), from the SELL records: bit j of mask
@@ -179,7 +181,8 @@ __global__ void __launch_bounds__(256) k_box_irregular(EuGridDev g, EuTablesDev 
 template <bool ROCKS, bool MULTIROCK, bool CAP, int NS, int MINB, bool SHARE>
 __global__ void __launch_bounds__(256, MINB)
 k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUtensorMap mapPc,
-           const __grid_constant__ CUtensorMap mapQG, const __grid_constant__ CUtensorMap mapT,
+           const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapG,
+           const __grid_constant__ CUtensorMap mapT,
            EuGridDev g, EuTablesDev t, EuFastDev f, EuStepArgs a, EuHaloDev halo, EuBoxDev b, int slice_lo, int slice_hi, int tab_bytes)
 {
     TabLayout L;
@@ -204,22 +207,29 @@ k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUt
     const int tx = b.tx, ty = b.ty, txp = tx + 2, txf = tx + 1, txs = tx + 4;      // row lengths: ring / T boxes, face boxes, S boxes
     const int lx = tid % tx, ly = tid/tx;
     const bool in_tile = tid < tx*ty;
-    // halo duty: threads 0 .. 2(tx+ty)-1 each own one halo cell of the ring buffers
+    // halo duty: 2(tx+ty) threads each own one halo cell of the ring buffers.  With SHARE the tx+ty threads of the edge
+    // faces sit in other warps (the block waits for its slowest warp at every barrier: no warp gets both extras)
+    const int n_halo = 2*(tx + ty), n_edge = tx + ty, n_thr = int(blockDim.x);
+    const int e0 = SHARE ? 0 : 0;                                // edge faces: threads e0 .. e0 + tx + ty - 1
+    const int h0 = (SHARE && ((n_edge + 31) & ~31) + n_halo <= n_thr) ? ((n_edge + 31) & ~31) : 0;
+    const int ht = tid - h0;                                    // halo duty: threads h0 .. h0 + 2(tx+ty) - 1
     int hx = 0, hy = 0;
-    bool has_halo = true;
-    if (tid < tx)                 { hx = tid;            hy = -1; }
-    else if (tid < 2*tx)          { hx = tid - tx;       hy = ty; }
-    else if (tid < 2*tx + ty)     { hx = -1;             hy = tid - 2*tx; }
-    else if (tid < 2*tx + 2*ty)   { hx = tx;             hy = tid - 2*tx - ty; }
+    bool has_halo = ht >= 0;
+    if (ht < tx)                 { hx = ht;            hy = -1; }
+    else if (ht < 2*tx)          { hx = ht - tx;       hy = ty; }
+    else if (ht < 2*tx + ty)     { hx = -1;            hy = ht - 2*tx; }
+    else if (ht < 2*tx + 2*ty)   { hx = tx;            hy = ht - 2*tx - ty; }
     else has_halo = false;
     // byte offsets of this thread's entries (ring buffers, S / pc boxes, face boxes, T boxes)
     const int o_ring = ((ly + 1)*txp + lx + 1)*E, o_ring_h = ((hy + 1)*txp + hx + 1)*E;
     const int o_rk = (ly + 1)*txp + lx + 1, o_rk_h = (hy + 1)*txp + hx + 1;
     const int o_S = ((ly + 1)*txs + lx + 2)*8, o_S_h = ((hy + 1)*txs + hx + 2)*8;
-    const int o_F = (ly*txf + lx)*16;
     const int o_T = (ly*txp + lx)*8;
     const int D = b.nx*b.ny;
-    const unsigned bundle_bytes = unsigned(txs*(ty + 2)*8*(CAP ? 2 : 1) + 3*txf*(ty + 1)*16 + (CAP ? 3*txp*(ty + 1)*8 : 0));
+    const int n_G = __popc(unsigned(b.g_mask) & 7u);
+    const unsigned bundle_bytes = unsigned(txs*(ty + 2)*8*(CAP ? 2 : 1) + (3 + n_G + (CAP ? 3 : 0))*txp*(ty + 1)*8);
+    const bool hgx = b.g_mask & 1, hgy = b.g_mask & 2, hgz = b.g_mask & 4;        // axis has gravity: its G box is loaded
+    const int oGx = b.off_G, oGy = b.off_G + (hgx ? b.T_bytes : 0), oGz = oGy + (hgy ? b.T_bytes : 0);     // G boxes present are packed
     const unsigned char* const stage0 = base + b.off_stage;
     unsigned char* const ring0 = base + b.off_lam;
     unsigned char* const rk0 = base + b.off_rk;
@@ -252,9 +262,12 @@ k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUt
         mbar_expect_tx(bar, bundle_bytes);
         tma_load_3d(st + b.off_S, &mapS, x0 - 2, y0 - 1, k + 1, bar);
         if (CAP) tma_load_3d(st + b.off_pc, &mapPc, x0 - 2, y0 - 1, k + 1, bar);
-        tma_load_4d(st + b.off_qg, &mapQG, 2*(x0 - 1), y0, k, 0, bar);
-        tma_load_4d(st + b.off_qg + b.qg_bytes, &mapQG, 2*x0, y0 - 1, k, 1, bar);
-        tma_load_4d(st + b.off_qg + 2*b.qg_bytes, &mapQG, 2*x0, y0, k, 2, bar);
+        tma_load_4d(st + b.off_q, &mapQ, x0 - 2, y0, k, 0, bar);
+        tma_load_4d(st + b.off_q + b.T_bytes, &mapQ, x0, y0 - 1, k, 1, bar);
+        tma_load_4d(st + b.off_q + 2*b.T_bytes, &mapQ, x0, y0, k, 2, bar);
+        if (hgx) tma_load_4d(st + oGx, &mapG, x0 - 2, y0, k, 0, bar);
+        if (hgy) tma_load_4d(st + oGy, &mapG, x0, y0 - 1, k, 1, bar);
+        if (hgz) tma_load_4d(st + oGz, &mapG, x0, y0, k, 2, bar);
         if (CAP) {
             tma_load_4d(st + b.off_T, &mapT, x0 - 2, y0, k, 0, bar);
             tma_load_4d(st + b.off_T + b.T_bytes, &mapT, x0, y0 - 1, k, 1, bar);
@@ -405,11 +418,12 @@ k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUt
                 const unsigned char* rkc = rk0 + r_cur*b.rk_bytes;
                 if (in_tile) {
                     if (p_update) finish_prev();
-                    const unsigned char* QG = st + b.off_qg + o_F;
+                    const unsigned char* QQ = st + b.off_q + o_T;          // q, G and T boxes share their indexing
                     const unsigned char* TT = st + b.off_T + o_T;
-                    const double2 qg5 = *reinterpret_cast<const double2*>(QG + 2*b.qg_bytes);
+                    const double q5 = *reinterpret_cast<const double*>(QQ + 2*b.T_bytes);
+                    const double G5 = hgz ? *reinterpret_cast<const double*>(st + oGz + o_T) : 0.0;
                     const double T5 = CAP ? *reinterpret_cast<const double*>(TT + 2*b.T_bytes) : 0.0;
-                    const double dS5 = box_face<ROCKS, MULTIROCK, CAP, true>(L, t, m, lw1, lo1, S1, pc1, rock1, qg5, T5);
+                    const double dS5 = box_face<ROCKS, MULTIROCK, CAP, true>(L, t, m, lw1, lo1, S1, pc1, rock1, q5, G5, hgz, T5);
                     if (update) {
                         // x+ and y+ faces: this cell is their lo cell
                         const double2 ex = *reinterpret_cast<const double2*>(ringc + o_ring + E);
@@ -424,10 +438,12 @@ k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUt
                             Typ = *reinterpret_cast<const double*>(TT + b.T_bytes + txp*8);
                             if (MULTIROCK) { rxp = int(rkc[o_rk + 1]); ryp = int(rkc[o_rk + txp]); }
                         }
-                        const double2 qx = *reinterpret_cast<const double2*>(QG + 16);
-                        const double2 qy = *reinterpret_cast<const double2*>(QG + b.qg_bytes + txf*16);
-                        const double dSx = box_face<ROCKS, MULTIROCK, CAP, true>(L, t, m, ex.x, ex.y, sx.x, sx.y, rxp, qx, Txp);
-                        const double dSy = box_face<ROCKS, MULTIROCK, CAP, true>(L, t, m, ey.x, ey.y, sy.x, sy.y, ryp, qy, Typ);
+                        const double qxp = *reinterpret_cast<const double*>(QQ + 16);
+                        const double qyp = *reinterpret_cast<const double*>(QQ + b.T_bytes + txp*8);
+                        const double Gxp = hgx ? *reinterpret_cast<const double*>(st + oGx + o_T + 16) : 0.0;
+                        const double Gyp = hgy ? *reinterpret_cast<const double*>(st + oGy + o_T + txp*8) : 0.0;
+                        const double dSx = box_face<ROCKS, MULTIROCK, CAP, true>(L, t, m, ex.x, ex.y, sx.x, sx.y, rxp, qxp, Gxp, hgx, Txp);
+                        const double dSy = box_face<ROCKS, MULTIROCK, CAP, true>(L, t, m, ey.x, ey.y, sy.x, sy.y, ryp, qyp, Gyp, hgy, Typ);
                         *reinterpret_cast<double*>(fxw + (ly*txf + lx + 1)*8) = dSx;
                         *reinterpret_cast<double*>(fyw + ((ly + 1)*tx + lx)*8) = dSy;
                         p_acc = ((m.dS4 - dS5) - dSx) - dSy + acc_irr;
@@ -437,9 +453,10 @@ k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUt
                     m.dS4 = dS5;
                 }
                 // the faces on the tile's low edges: thread i < tx the y- face of cell (i, 0), thread tx + j the x- face of (0, j)
-                if (tid < tx + ty && k >= z0) {
-                    const bool yedge = tid < tx;
-                    const int i = yedge ? tid : 0, j = yedge ? 0 : tid - tx;
+                if (tid >= e0 && tid < e0 + n_edge && k >= z0) {
+                    const int et = tid - e0;
+                    const bool yedge = et < tx;
+                    const int i = yedge ? et : 0, j = yedge ? 0 : et - tx;
                     const int hi_idx = (j + 1)*txp + i + 1;                       // ring entry of the tile cell (the face's hi cell)
                     const int lo_idx = yedge ? hi_idx - txp : hi_idx - 1;       // halo cell below / to the left (the lo cell)
                     const double2 el = *reinterpret_cast<const double2*>(ringc + lo_idx*E);
@@ -457,20 +474,23 @@ k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUt
                         Tf = yedge ? *reinterpret_cast<const double*>(st + b.off_T + b.T_bytes + i*8)
                                    : *reinterpret_cast<const double*>(st + b.off_T + (j*txp + 1)*8);
                     }
-                    const double2 qf = yedge ? *reinterpret_cast<const double2*>(st + b.off_qg + b.qg_bytes + i*16)
-                                             : *reinterpret_cast<const double2*>(st + b.off_qg + j*txf*16);
-                    const double dSe = box_face<ROCKS, MULTIROCK, CAP, true>(L, t, ml, eh.x, eh.y, sh.x, sh.y, rh, qf, Tf);
+                    const int eo = yedge ? i*8 : (j*txp + 1)*8;           // entry of the edge face in its q / G / T box
+                    const double qe = *reinterpret_cast<const double*>(st + b.off_q + (yedge ? b.T_bytes : 0) + eo);
+                    const bool ge = yedge ? hgy : hgx;
+                    const double Ge = ge ? *reinterpret_cast<const double*>(st + (yedge ? oGy : oGx) + eo) : 0.0;
+                    const double dSe = box_face<ROCKS, MULTIROCK, CAP, true>(L, t, ml, eh.x, eh.y, sh.x, sh.y, rh, qe, Ge, ge, Tf);
                     if (yedge) *reinterpret_cast<double*>(fyw + i*8) = dSe;
                     else       *reinterpret_cast<double*>(fxw + j*txf*8) = dSe;
                 }
                 fpar ^= 1;
             } else
             if (in_tile) {
-                const unsigned char* QG = st + b.off_qg + o_F;
+                const unsigned char* QQ = st + b.off_q + o_T;              // q, G and T boxes share their indexing
                 const unsigned char* TT = st + b.off_T + o_T;
-                const double2 qg5 = *reinterpret_cast<const double2*>(QG + 2*b.qg_bytes);
+                const double q5 = *reinterpret_cast<const double*>(QQ + 2*b.T_bytes);
+                const double G5 = hgz ? *reinterpret_cast<const double*>(st + oGz + o_T) : 0.0;
                 const double T5 = CAP ? *reinterpret_cast<const double*>(TT + 2*b.T_bytes) : 0.0;
-                const double dS5 = box_face<ROCKS, MULTIROCK, CAP, true>(L, t, m, lw1, lo1, S1, pc1, rock1, qg5, T5);
+                const double dS5 = box_face<ROCKS, MULTIROCK, CAP, true>(L, t, m, lw1, lo1, S1, pc1, rock1, q5, G5, hgz, T5);
                 if (update) {
                     const unsigned char* ring = ring0 + r_cur*b.lam_bytes + o_ring;
                     const unsigned char* rk = rk0 + r_cur*b.rk_bytes + o_rk;
@@ -479,7 +499,6 @@ k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUt
                     // the operands come from shared memory, their latency is covered by the other warps)
                     const int dr[4] = { -E, E, -txp*E, txp*E };
                     const int dk[4] = { -1, 1, -txp, txp };
-                    const int dq[4] = { 0, 16, b.qg_bytes, b.qg_bytes + txf*16 };
                     const int dt[4] = { 8, 16, b.T_bytes, b.T_bytes + txp*8 };
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
@@ -492,9 +511,11 @@ k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUt
                             rq = MULTIROCK ? int(rk[dk[q]]) : 0;
                             Tq = *reinterpret_cast<const double*>(TT + dt[q]);
                         }
-                        const double2 qgq = *reinterpret_cast<const double2*>(QG + dq[q]);
-                        if (q & 1) acc -= box_face<ROCKS, MULTIROCK, CAP, true>(L, t, m, e.x, e.y, e2.x, e2.y, rq, qgq, Tq);
-                        else       acc += box_face<ROCKS, MULTIROCK, CAP, false>(L, t, m, e.x, e.y, e2.x, e2.y, rq, qgq, Tq);
+                        const double qq = *reinterpret_cast<const double*>(QQ + dt[q]);
+                        const bool gq = q < 2 ? hgx : hgy;
+                        const double Gq = gq ? *reinterpret_cast<const double*>(st + (q < 2 ? oGx : oGy) + o_T + (dt[q] - (q < 2 ? 0 : b.T_bytes))) : 0.0;
+                        if (q & 1) acc -= box_face<ROCKS, MULTIROCK, CAP, true>(L, t, m, e.x, e.y, e2.x, e2.y, rq, qq, Gq, gq, Tq);
+                        else       acc += box_face<ROCKS, MULTIROCK, CAP, false>(L, t, m, e.x, e.y, e2.x, e2.y, rq, qq, Gq, gq, Tq);
                     }
                     acc += acc_irr;
                     OwnMob<false> own0;
