@@ -932,7 +932,8 @@ struct EuBoxPlan {
     CUtensorMap mapS[2], mapPc[2], mapQ, mapG, mapT;
     int g_mask = 7;                                  // axis planes with a gravity component (set after the contraction)
     int4* d_units = nullptr;
-    int n_units = 0, n_bnd_units[2] = { 0, 0 }, n_flagged = 0;
+    int* d_unit_start = nullptr;                    // [n_blocks + 1] unit range of each block
+    int n_units = 0, n_blocks = 0, n_bnd_units[2] = { 0, 0 }, n_flagged = 0;
     int units_key[5] = { -1, -1, -1, -1, -1 };      // (bnd planes lo, hi, grid blocks, lz override, cap) the unit list was built for
     const unsigned short* cmask = nullptr;
     int g_mask_seen = -1;
@@ -1017,6 +1018,7 @@ void eu_box_plan_destroy(EuBoxPlan* p)
 {
     if (!p) return;
     if (p->d_units) cudaFree(p->d_units);
+    if (p->d_unit_start) cudaFree(p->d_unit_start);
     delete p;
 }
 
@@ -1104,41 +1106,105 @@ static int box_chunks(const EuBoxPlan* p, int grid_blocks, int lz_env, int min_l
     return best_chunks;
 }
 
+// EU_BOX_UNITS (tuning knob, read at every plan build): "chunks" (default) or "spans".
+//   chunks  every tile's planes cut into the same number of z-chunks (box_chunks), handed out round-robin.  A block may
+//           do one unit more than another, but the blocks of one SM share its issue slots, so what counts is the sum
+//           per SM, and that differs by one unit in ~40
+//   spans   the (tile, plane) pairs in tile-major order cut into one span of equal length per block; a span is split into
+//           units at tile boundaries, and a cut closer than min_piece planes to a tile boundary moves onto it (so the
+//           planes next to a slab boundary stay in ONE unit per tile, as the unit counters of the exchange assume).
+//           Measured (profiles/README.md, r04a): 512x512x256 2.6 % slower than chunks (neighbouring tiles are no longer
+//           swept at the same time: less halo reuse in L2), 32-plane slab 1.5 % faster, C3 0.7 % faster
+static int box_units_mode()
+{
+    const char* e = getenv("EU_BOX_UNITS");
+    return (e && std::strcmp(e, "spans") == 0) ? 1 : 0;
+}
+
 static int box_build_units(EuBoxPlan* p, int bnd_lo, int bnd_hi, int grid_blocks, bool cap)
 {
     const char* e = getenv("EU_BOX_LZ");
     const int lz_env = e ? atoi(e) : 0;
-    if (p->units_key[0] == bnd_lo && p->units_key[1] == bnd_hi && p->units_key[2] == grid_blocks && p->units_key[3] == lz_env &&
+    const int mode = box_units_mode();
+    const int lz_key = lz_env + 100000*mode;
+    if (p->units_key[0] == bnd_lo && p->units_key[1] == bnd_hi && p->units_key[2] == grid_blocks && p->units_key[3] == lz_key &&
         p->units_key[4] == int(cap) && p->d_units) return 0;
-    const int tiles_x = (p->nx + p->tx - 1)/p->tx, tiles_y = (p->ny + p->ty - 1)/p->ty;
+    const int tiles_x = (p->nx + p->tx - 1)/p->tx, tiles_y = (p->ny + p->ty - 1)/p->ty, tiles = tiles_x*tiles_y;
     const int planes = p->z_hi - p->z_lo;
-    const int chunks = box_chunks(p, grid_blocks, lz_env, std::max(bnd_lo, bnd_hi));
-    std::vector<int4> units;
-    auto add = [&](int q) {
-        const int z0 = p->z_lo + int((long long)planes*q/chunks), z1 = p->z_lo + int((long long)planes*(q + 1)/chunks);
-        const int flags = ((bnd_lo > 0 && q == 0) ? 1 : 0) | ((bnd_hi > 0 && q == chunks - 1) ? 2 : 0);
-        if (z1 <= z0) return;
-        for (int tyi = 0; tyi < tiles_y; ++tyi)
-            for (int txi = 0; txi < tiles_x; ++txi)
-                units.push_back(make_int4((txi*p->tx) | ((tyi*p->ty) << 16), z0, z1, flags));
+    std::vector<int4> units;            // block after block, a block's flagged units first
+    std::vector<int> start;             // [blocks + 1]
+    auto unit_of = [&](int tile, int s, int e2) {
+        const int txi = tile % tiles_x, tyi = tile/tiles_x;
+        const int flags = ((bnd_lo > 0 && s == 0) ? 1 : 0) | ((bnd_hi > 0 && e2 == planes) ? 2 : 0);
+        return make_int4((txi*p->tx) | ((tyi*p->ty) << 16), p->z_lo + s, p->z_lo + e2, flags);
     };
-    // flagged chunks first
-    if (bnd_lo > 0) add(0);
-    if (bnd_hi > 0 && (chunks > 1 || bnd_lo == 0)) add(chunks - 1);
-    for (int q = 0; q < chunks; ++q) {
-        if ((bnd_lo > 0 && q == 0) || (bnd_hi > 0 && q == chunks - 1)) continue;
-        add(q);
+    if (tiles > 0 && planes > 0 && (mode == 0 || lz_env > 0 || bnd_lo > 0 || bnd_hi > 0)) {        // (spans: single-rank runs only)
+        const int chunks = box_chunks(p, grid_blocks, lz_env, std::max(bnd_lo, bnd_hi));
+        std::vector<int4> flat;
+        auto add = [&](int q) {
+            const int s = int((long long)planes*q/chunks), e2 = int((long long)planes*(q + 1)/chunks);
+            if (e2 <= s) return;
+            for (int tile = 0; tile < tiles; ++tile) flat.push_back(unit_of(tile, s, e2));
+        };
+        // flagged chunks first
+        if (bnd_lo > 0) add(0);
+        if (bnd_hi > 0 && (chunks > 1 || bnd_lo == 0)) add(chunks - 1);
+        for (int q = 0; q < chunks; ++q) {
+            if ((bnd_lo > 0 && q == 0) || (bnd_hi > 0 && q == chunks - 1)) continue;
+            add(q);
+        }
+        const int blocks = std::max(1, std::min(grid_blocks, int(flat.size())));
+        for (int i = 0; i < blocks; ++i) {
+            start.push_back(int(units.size()));
+            for (size_t u = size_t(i); u < flat.size(); u += size_t(blocks)) units.push_back(flat[u]);
+        }
+        start.push_back(int(units.size()));
+    } else if (tiles > 0 && planes > 0) {
+        const long long W = (long long)tiles*planes;
+        const int min_piece = std::max(std::max(bnd_lo, bnd_hi), 3);
+        const int blocks = int(std::max(1LL, std::min((long long)grid_blocks, W/4)));
+        std::vector<long long> cut(size_t(blocks) + 1);
+        for (int i = 0; i <= blocks; ++i) {
+            const long long pos = W*i/blocks;
+            long long tile = pos/planes;
+            int s = int(pos % planes);
+            if (s < min_piece) s = 0;
+            else if (s > planes - min_piece) { s = 0; ++tile; }
+            cut[size_t(i)] = tile*planes + s;
+        }
+        cut[0] = 0; cut[size_t(blocks)] = W;
+        for (int i = 0; i < blocks; ++i) {
+            start.push_back(int(units.size()));
+            const size_t first = units.size();
+            for (long long pos = cut[size_t(i)]; pos < cut[size_t(i) + 1]; ) {
+                const int tile = int(pos/planes), s = int(pos % planes);
+                const int e2 = int(std::min((long long)planes, s + (cut[size_t(i) + 1] - pos)));
+                units.push_back(unit_of(tile, s, e2));
+                pos += e2 - s;
+            }
+            std::stable_partition(units.begin() + first, units.end(), [](const int4& un) { return un.w != 0; });
+        }
+        start.push_back(int(units.size()));
     }
-    p->n_bnd_units[0] = bnd_lo > 0 ? tiles_x*tiles_y : 0;
-    p->n_bnd_units[1] = bnd_hi > 0 ? tiles_x*tiles_y : 0;
+    p->n_bnd_units[0] = p->n_bnd_units[1] = 0;
     p->n_flagged = 0;
-    for (const int4& un : units) if (un.w) ++p->n_flagged;
+    for (const int4& un : units) {
+        if (un.w) ++p->n_flagged;
+        if (un.w & 1) ++p->n_bnd_units[0];
+        if (un.w & 2) ++p->n_bnd_units[1];
+    }
+    // the exchange counts ONE finished unit per tile and boundary (eu_box_plan_units)
+    if ((bnd_lo > 0 && p->n_bnd_units[0] != tiles) || (bnd_hi > 0 && p->n_bnd_units[1] != tiles)) return -1;
     if (p->d_units) { cudaFree(p->d_units); p->d_units = nullptr; }
+    if (p->d_unit_start) { cudaFree(p->d_unit_start); p->d_unit_start = nullptr; }
     p->n_units = int(units.size());
+    p->n_blocks = start.empty() ? 0 : int(start.size()) - 1;
     if (units.empty()) return 0;
     if (cudaMalloc((void**)&p->d_units, units.size()*sizeof(int4)) != cudaSuccess) return -1;
     if (cudaMemcpy(p->d_units, units.data(), units.size()*sizeof(int4), cudaMemcpyHostToDevice) != cudaSuccess) return -1;
-    p->units_key[0] = bnd_lo; p->units_key[1] = bnd_hi; p->units_key[2] = grid_blocks; p->units_key[3] = lz_env; p->units_key[4] = int(cap);
+    if (cudaMalloc((void**)&p->d_unit_start, start.size()*sizeof(int)) != cudaSuccess) return -1;
+    if (cudaMemcpy(p->d_unit_start, start.data(), start.size()*sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) return -1;
+    p->units_key[0] = bnd_lo; p->units_key[1] = bnd_hi; p->units_key[2] = grid_blocks; p->units_key[3] = lz_key; p->units_key[4] = int(cap);
     return 0;
 }
 
@@ -1206,6 +1272,7 @@ static int launch_box(EuBoxPlan* p, const EuGridDev& g, const EuTablesDev& t, co
     lay.b.n_units = p->n_units;
     lay.b.cmask = p->cmask;
     lay.b.n_flagged = p->n_flagged;
+    lay.b.unit_start = p->d_unit_start;
     lay.b.acc_irr = p->acc_irr;
     int launches = 1;
     if (p->n_irr > 0) {
@@ -1214,7 +1281,7 @@ static int launch_box(EuBoxPlan* p, const EuGridDev& g, const EuTablesDev& t, co
         k_box_irregular<ROCKS, MULTIROCK, CAP><<<ib, 256, tab_bytes, st>>>(g, t, f, a, halo, p->irr_cells, p->n_irr, p->cmask, p->acc_irr);
         ++launches;
     }
-    const int blocks = std::min(grid_full, p->n_units);
+    const int blocks = p->n_blocks;
     kern<<<blocks, p->threads, lay.total, st>>>(p->mapS[cur], p->mapPc[cur], p->mapQ, p->mapG, p->mapT, g, t, f, a, halo, lay.b, slice_lo, slice_hi, (int)tab_bytes);
     return launches;
 }

@@ -40,7 +40,8 @@ struct EuBoxDev {
     int g_mask;                                   // bit a: the faces of axis plane a have a gravity component somewhere (G box loaded)
     int off_fx, off_fy, fx_bytes, fy_bytes;       // SHARE: two buffers each of x+ fluxes [ty][tx+1] and y+ fluxes [ty+1][tx]
     int T_bytes;                                  // one axis' box of q, G or T
-    int n_flagged;                // units with a push flag (they are the first of the list)
+    int n_flagged;                // units with a push flag
+    const int* unit_start;        // [blocks + 1] block i sweeps units[unit_start[i] .. unit_start[i+1]), flagged ones first
     const unsigned short* cmask;  // per cell: record slots with faces outside the axis planes
     const double* acc_irr;        // per cell with a non-zero mask: sum of those faces' contributions (k_box_irregular)
 };
@@ -235,9 +236,10 @@ k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUt
     unsigned char* const rk0 = base + b.off_rk;
     int slot = 0;                                               // stage of the current bundle; par = phase parity of its mbarrier
     unsigned par = 0;
-    if (halo.enabled && int(blockIdx.x) < b.n_flagged && tid < halo.n_wait) {
+    const int u_begin = __ldg(b.unit_start + blockIdx.x), u_end = __ldg(b.unit_start + blockIdx.x + 1);
+    if (halo.enabled && u_begin < u_end && (__ldg(&b.units[u_begin].w) & 3) && tid < halo.n_wait) {
         // this block sweeps planes next to a slab boundary: the ghosts of the previous substep must have landed before
-        // any TMA load reads them (flagged units are the first of the list, so every block that has one gets here)
+        // any TMA load reads them (flagged units are the first of a block's list, so every block that has one gets here)
         const volatile unsigned* fl = halo.my_flags + halo.wait_rank[tid];
         const long long t0 = clock64();
         while ((int)(*fl - (halo.epoch - 1u)) < 0) {
@@ -250,11 +252,12 @@ k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUt
     // ---- producer (thread 0): one bundle per plane, NS - 1 planes ahead of the sweep, ACROSS work units -- the first
     // bundles of the next unit are already in flight while the last planes of the current one are swept
     // (its state lives in shared memory, behind the mbarriers: no registers of the sweep are spent on it)
-    struct Producer { int4 unit, next; int pu, pk, slot, pad; };
+    struct Producer { int4 unit, next; int pu, pk, slot, end; };
     Producer* const P = reinterpret_cast<Producer*>(base + b.off_bar + 64);
     auto produce = [&]() {
         int pu = P->pu;
-        if (pu >= b.n_units) return;
+        const int pend = P->end;
+        if (pu >= pend) return;
         const int4 un = P->unit;
         const int x0 = un.x & 0xffff, y0 = un.x >> 16, k = P->pk, ps = P->slot;
         const unsigned bar = base_u32 + b.off_bar + 8*ps;
@@ -275,30 +278,30 @@ k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUt
         }
         P->slot = (ps + 1 == NS) ? 0 : ps + 1;
         if (k + 1 >= un.z) {                                    // on to the block's next unit
-            pu += gridDim.x;
+            ++pu;
             P->pu = pu;
             const int4 nx = P->next;
             P->unit = nx;
             P->pk = nx.y - 1;
-            if (pu + int(gridDim.x) < b.n_units) P->next = __ldg(b.units + pu + gridDim.x);
+            if (pu + 1 < pend) P->next = __ldg(b.units + pu + 1);
         } else {
             P->pk = k + 1;
         }
     };
     if (tid == 0) {
-        const int pu = blockIdx.x;
-        P->pu = pu; P->slot = 0;
+        const int pu = u_begin;
+        P->pu = pu; P->slot = 0; P->end = u_end;
         int4 un = make_int4(0, 0, 0, 0);
-        if (pu < b.n_units) un = __ldg(b.units + pu);
+        if (pu < u_end) un = __ldg(b.units + pu);
         P->unit = un;
         P->pk = un.y - 1;
-        if (pu + int(gridDim.x) < b.n_units) P->next = __ldg(b.units + pu + gridDim.x);
+        if (pu + 1 < u_end) P->next = __ldg(b.units + pu + 1);
         for (int j = 0; j < NS; ++j) produce();
     }
     bool first_step = true;                                     // nothing to refill at the block's very first step
     unsigned done0 = 0u, done1 = 0u;                            // finished units of this block with pushes to range A / B
 
-    for (int u = blockIdx.x; u < b.n_units; u += gridDim.x) {
+    for (int u = u_begin; u < u_end; ++u) {
         const int4 unit = __ldg(b.units + u);
         const int x0 = unit.x & 0xffff, y0 = unit.x >> 16, z0 = unit.y, z1 = unit.z;
         const int push = unit.w & 3;
@@ -316,16 +319,18 @@ k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUt
         }
         Mob<ROCKS, MULTIROCK>::both(L, t, m.rock0, m.S0, m.lw0, m.lo0);
         // halo cell: its cell index in plane k (or -1 outside the grid), for the rock id
-        int hc = -1;
+        int hc = 0;                                             // (negative in plane -1: validity is a flag of its own)
+        bool h_ok = false;
         if (MULTIROCK && has_halo) {
             const int qx = x0 + hx, qy = y0 + hy;
-            if (qx >= 0 && qx < b.nx && qy >= 0 && qy < b.ny) hc = qx + b.nx*qy + (z0 - 1)*D;
+            h_ok = qx >= 0 && qx < b.nx && qy >= 0 && qy < b.ny;
+            hc = qx + b.nx*qy + (z0 - 1)*D;
         }
         unsigned mk = 0u;                                       // mask of the faces outside the axis planes, plane k (none for z0-1)
         int rock_n = 0, rock_hn = 0;                            // rock ids of plane k+1: own cell, halo cell
         if (MULTIROCK && z0 < b.nz) {
             if (active) rock_n = __ldg(f.rock8 + c + D);
-            if (hc >= 0) rock_hn = __ldg(f.rock8 + hc + D);
+            if (h_ok) rock_hn = __ldg(f.rock8 + hc + D);
         }
         // ring buffers: next (plane k+1, written in phase A), cur (plane k, read in phase B), and the one in between
         int r_next = ((z0 % 3) + 3) % 3, r_cur = (r_next + 2) % 3;
@@ -378,7 +383,7 @@ k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUt
             if (MULTIROCK) {
                 const bool up2 = k + 2 < b.nz;
                 rock_n = (active && up2) ? int(__ldg(f.rock8 + c + 2*D)) : 0;
-                rock_hn = (hc >= 0 && up2) ? int(__ldg(f.rock8 + hc + 2*D)) : 0;
+                rock_hn = (h_ok && up2) ? int(__ldg(f.rock8 + hc + 2*D)) : 0;
             }
             const unsigned char* st = stage0 + slot*b.stage_bytes;
             mbar_wait(base_u32 + b.off_bar + 8*slot, par);
@@ -541,7 +546,7 @@ k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUt
             }
             m.S0 = S1; m.lw0 = lw1; m.lo0 = lo1; m.rock0 = rock1; m.pc0 = pc1;
             c += D;
-            if (MULTIROCK && hc >= 0) hc += D;
+            if (MULTIROCK) hc += D;
             ++slot;
             if (slot == NS) { slot = 0; par ^= 1u; }
             r_cur = r_next;
@@ -555,8 +560,8 @@ k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUt
             if (push & 1) ++done0;
             if (push & 2) ++done1;
         }
-        if ((done0 | done1) && u + int(gridDim.x) >= b.n_flagged) {
-            // this was the block's last unit with pushes (they are the first of the list): all of them are ordered
+        if ((done0 | done1) && (u + 1 >= u_end || (__ldg(&b.units[u + 1].w) & 3) == 0)) {
+            // this was the block's last unit with pushes (they are the first of its list): all of them are ordered
             // before thread 0 by the block barrier, its ONE system-scope fence is cumulative, then the finished-unit
             // counters of the two ranges (a fence per unit held the whole block back for its NVLink round trip)
             __syncthreads();

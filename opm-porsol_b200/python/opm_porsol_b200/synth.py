@@ -448,14 +448,16 @@ def lognormal_perm(N, seed, mean_md=100.0, sigma=1.0, kz_ratio=0.1):
     return perm
 
 
-def config_c3(nx=256, ny=256, nz=128, seed=42):
-    """Faulted corner-point grid, lognormal K, 3 rock types in layer bands, V+G+C."""
+def config_c3(nx=256, ny=256, nz=128, seed=42, random_rocks=False):
+    """Faulted corner-point grid, lognormal K, 3 rock types in layer bands (or drawn per cell), V+G+C."""
     fi = [(nx//4, 1.5), (nx//2, 2.25), (3*nx//4, 0.75)]
     fj = [(ny//2, 3.0)]
     g = faulted_grid(nx, ny, nz, 10.0, 10.0, 1.0, faults_i=fi, faults_j=fj)
     N = g["N"]
     k = np.arange(N)//(nx*ny)
     rock_id = np.minimum((3*k)//nz, 2).astype(np.int32)
+    if random_rocks:
+        rock_id = np.minimum((3.0*mt_uniform(seed + 3, N)).astype(np.int32), 2)
     rocks = [corey_table(24, 0.10, 0.10, 0.30), corey_table(20, 0.15, 0.05, 0.22), corey_table(28, 0.05, 0.20, 0.40)]
     sat0 = 0.25 + 0.1*(mt_uniform(seed + 2, N) - 0.5)
     return make_case("C3", g, poro=0.05 + 0.25*mt_uniform(seed + 1, N), perm=lognormal_perm(N, seed),

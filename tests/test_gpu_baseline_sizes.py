@@ -111,6 +111,20 @@ def test_c4_slab_capillary_march_vs_oracle():
         _device_check(case, ref, mode, expect_march="box")
 
 
+@pytest.mark.parametrize("units", ["chunks", "spans"])
+def test_rock_ids_drawn_per_cell_vs_oracle(units, monkeypatch):
+    """Three rock types drawn per cell on a faulted grid of several tiles: the rock ids of a tile's halo cells differ from
+    its own cells' in every plane, from plane 0 on (the layer bands of C3 do not test that).  Also with the other way of
+    cutting the sweep into work units (EU_BOX_UNITS=spans: units of unequal length, several per tile column)."""
+    from opm_porsol_b200 import synth
+    monkeypatch.setenv("EU_BOX_UNITS", units)
+    case = synth.config_c3(96, 40, 10, random_rocks=True)
+    assert len(np.unique(case.rock_id[:96*40])) == 3
+    ref = _oracle_run(case, n_sub=3, solve_steps=6, cfl_fraction=0.25)
+    for mode in ("fast", "strict"):
+        _device_check(case, ref, mode, expect_march="box" if mode == "fast" else False)
+
+
 def test_c2_full_size_vs_oracle():
     """BASELINE config 1 at its stated size: 100^3 Cartesian, rotated anisotropic K, rock table, V+G+C."""
     from opm_porsol_b200 import synth
@@ -120,7 +134,7 @@ def test_c2_full_size_vs_oracle():
     _device_check(case, ref, "strict", expect_march=False)
 
 
-def test_c3_full_size_vs_oracle():
+def test_c3_full_size_vs_oracle(monkeypatch):
     """BASELINE config 2 at its stated size: 256 x 256 x 128 faulted corner-point, lognormal K, 3 rocks, V+G+C:
     two substeps of the whole 8.4 M-cell grid against the oracle."""
     from opm_porsol_b200 import synth
@@ -128,3 +142,5 @@ def test_c3_full_size_vs_oracle():
     ref = _oracle_run(case, n_sub=2, solve_steps=0, cfl_fraction=0.25)
     _device_check(case, ref, "fast", expect_march="box")          # fault faces through the pre-pass kernel
     _device_check(case, ref, "strict", expect_march=False)
+    monkeypatch.setenv("EU_BOX_UNITS", "spans")                   # units of up to 110 planes that cross the rock bands
+    _device_check(case, ref, "fast", expect_march="box")
