@@ -1275,14 +1275,37 @@ static int launch_box(EuBoxPlan* p, const EuGridDev& g, const EuTablesDev& t, co
     lay.b.unit_start = p->d_unit_start;
     lay.b.acc_irr = p->acc_irr;
     int launches = 1;
+    // EU_PDL (tuning knob, default 0): programmatic dependent launch -- a kernel's blocks may take their SM slots and run
+    // their prologue (rock tables to shared memory, mbarrier set-up) while the previous kernel of the stream drains;
+    // griddepcontrol.wait in the kernels orders every access to substep data behind the previous kernel's completion.
+    // Measured (profiles/README.md, r04b): correct (all GPU tests pass with it) but SLOWER -- the sweep without the
+    // capillary term 1.12 -> 1.69 ms per substep at 512x512x256, as if one of its three blocks per SM came too late
+    // (early blocks of the next pre-pass hold registers); with the capillary term (two blocks per SM) no change.  Off.
+    static int pdl = -1;
+    if (pdl < 0) { const char* e = getenv("EU_PDL"); pdl = e ? (atoi(e) != 0) : 0; }
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl;
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.blockDim = dim3(256);
+    cfg.stream = st;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
     if (p->n_irr > 0) {
         // pre-pass: faces outside the axis planes, summed per cell
         const int ib = std::min((p->n_irr + 255)/256, p->n_sms*8);
-        k_box_irregular<ROCKS, MULTIROCK, CAP><<<ib, 256, tab_bytes, st>>>(g, t, f, a, halo, p->irr_cells, p->n_irr, p->cmask, p->acc_irr);
+        cfg.gridDim = dim3(ib);
+        cfg.dynamicSmemBytes = tab_bytes;
+        const int* irr_cells = p->irr_cells;
+        const unsigned short* cmask = p->cmask;
+        if (cudaLaunchKernelEx(&cfg, k_box_irregular<ROCKS, MULTIROCK, CAP>, g, t, f, a, halo, irr_cells, p->n_irr, cmask, p->acc_irr) != cudaSuccess) return -1;
         ++launches;
     }
-    const int blocks = p->n_blocks;
-    kern<<<blocks, p->threads, lay.total, st>>>(p->mapS[cur], p->mapPc[cur], p->mapQ, p->mapG, p->mapT, g, t, f, a, halo, lay.b, slice_lo, slice_hi, (int)tab_bytes);
+    cfg.gridDim = dim3(p->n_blocks);
+    cfg.blockDim = dim3(p->threads);
+    cfg.dynamicSmemBytes = lay.total;
+    if (cudaLaunchKernelEx(&cfg, kern, p->mapS[cur], p->mapPc[cur], p->mapQ, p->mapG, p->mapT, g, t, f, a, halo, lay.b, slice_lo, slice_hi, (int)tab_bytes) != cudaSuccess) return -1;
     return launches;
 }
 

@@ -81,6 +81,13 @@ __device__ __forceinline__ void tma_load_4d(unsigned dst, const CUtensorMap* map
                  :: "r"(dst), "l"(map), "r"(x), "r"(y), "r"(z), "r"(w), "r"(bar) : "memory");
 }
 
+// Programmatic dependent launch (EU_PDL=1, off by default: measured slower, see launch_box): the next kernel of the
+// stream may start -- take its SM slots, copy the rock tables to shared memory, set up its mbarriers -- while this one
+// drains; it touches nothing a substep writes before pdl_wait(), which returns when the whole previous grid has finished
+// and its stores are visible.  Without the launch attribute both instructions do nothing.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // G == 0 (no gravity component through the face: every lateral face of a grid with horizontal layers): both phases are
 // upwinded by the sign of q alone.  Bit-identical to face_regular for G == 0.
 template <bool OWN, bool CAP>
@@ -150,7 +157,9 @@ __global__ void __launch_bounds__(256) k_box_irregular(EuGridDev g, EuTablesDev 
 {
     TabLayout L;
     L.nn = t.n_nodes_total; L.nb = t.n_buckets; L.nbd = double(t.n_buckets);
+    pdl_launch_dependents();
     if (ROCKS) tables_to_smem(t);
+    pdl_wait();
     if (halo.enabled && threadIdx.x < halo.n_wait) {
         // some of these faces may look at ghost cells: the previous substep's pushes must have landed
         const volatile unsigned* fl = halo.my_flags + halo.wait_rank[threadIdx.x];
@@ -188,6 +197,7 @@ k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUt
 {
     TabLayout L;
     L.nn = t.n_nodes_total; L.nb = t.n_buckets; L.nbd = double(t.n_buckets);
+    pdl_launch_dependents();
     if (ROCKS) tables_to_smem(t);
     // 128-aligned base of the staging area behind the tables
     const unsigned base_u32 = (smem_u32(eu_smem) + unsigned(tab_bytes) + 127u) & ~127u;
@@ -199,6 +209,7 @@ k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUt
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
+    pdl_wait();                                                 // from here on the previous kernel's results are read
     if (!halo.enabled) {
         const unsigned long long key = *a.fail_key;
         if (key != ~0ULL && (unsigned)(key >> 32) < (unsigned)a.substep) return;
