@@ -1390,7 +1390,7 @@ int eu_grid_end(eu_handle h)
         EU_CUDA(h, cudaMemsetAsync(h->d_qa.p, 0, 3*n*sizeof(double), h->st));
         EU_CUDA(h, cudaMemsetAsync(h->d_Ga.p, 0, 3*n*sizeof(double), h->st));
         h->box = eu_box_plan_create(nx, ny, nz, h->own_lo/h->axis[2], h->own_hi/h->axis[2], h->d_S[0].p, h->d_S[1].p, h->d_pc[0].p,
-                                    h->d_pc[1].p, h->d_qa.p, h->d_Ga.p, h->d_T.p, h->d_cmask.p, h->d_irr_cells.p, n_irr, h->d_acc_irr.p, h->n_sms);
+                                    h->d_pc[1].p, h->d_qa.p, h->d_Ga.p, h->d_T.p, h->d_cmask.p, h->d_irr_cells.p, n_irr, h->d_acc_irr.p, h->d_inv_porevol.p, h->n_sms);
     }
     EU_CUDA(h, cudaStreamSynchronize(h->st));
     EU_CUDA(h, cudaGetLastError());

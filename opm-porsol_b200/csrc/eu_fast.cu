@@ -929,7 +929,7 @@ __global__ void __launch_bounds__(kBlock) k_fast_state(EuGridDev g, EuTablesDev 
 struct EuBoxPlan {
     int nx = 0, ny = 0, nz = 0, z_lo = 0, z_hi = 0, n_local = 0;
     int tx = 0, ty = 0, threads = 0;
-    CUtensorMap mapS[2], mapPc[2], mapQ, mapG, mapT;
+    CUtensorMap mapS[2], mapPc[2], mapQ, mapG, mapT, mapA, mapV;     // A: acc_irr, V: 1 / pore volume
     int g_mask = 7;                                  // axis planes with a gravity component (set after the contraction)
     int4* d_units = nullptr;
     int* d_unit_start = nullptr;                    // [n_blocks + 1] unit range of each block
@@ -999,7 +999,10 @@ BoxLayout box_layout(const EuBoxPlan& p, bool cap, bool multirock, int stages, s
     b.off_q = S_bytes*(cap ? 2 : 1);
     b.off_G = b.off_q + 3*b.T_bytes;
     b.off_T = b.off_G + n_G*b.T_bytes;
-    b.stage_bytes = b.off_T + (cap ? 3*b.T_bytes : 0);
+    b.A_bytes = r128(p.tx*p.ty*8);                           // tile boxes of acc_irr and 1 / pore volume
+    b.off_A = b.off_T + (cap ? 3*b.T_bytes : 0);
+    b.off_V = b.off_A + b.A_bytes;
+    b.stage_bytes = b.off_V + b.A_bytes;
     b.off_bar = 0;
     b.off_lam = 128;
     b.off_rk = b.off_lam + 3*b.lam_bytes;
@@ -1024,7 +1027,8 @@ void eu_box_plan_destroy(EuBoxPlan* p)
 
 // nullptr when the box kernel does not apply (then the slice-class kernel runs)
 EuBoxPlan* eu_box_plan_create(int nx, int ny, int nz, int z_lo, int z_hi, double* S0, double* S1, double* pc0, double* pc1,
-                              double* qa, double* Ga, double* T, const unsigned short* cmask, const int* irr_cells, int n_irr, double* acc_irr, int n_sms)
+                              double* qa, double* Ga, double* T, const unsigned short* cmask, const int* irr_cells, int n_irr, double* acc_irr,
+                              double* inv_porevol, int n_sms)
 {
     // TMA: global strides are multiples of 16 bytes (nx even); coordinates fit the unit encoding
     if (nx < 2 || (nx & 1) || ny < 1 || nz < 1 || nx > 65535 || ny > 32767) return nullptr;
@@ -1064,6 +1068,9 @@ EuBoxPlan* eu_box_plan_create(int nx, int ny, int nz, int z_lo, int z_hi, double
         cuuint32_t box[3] = { cuuint32_t(p->tx + 4), cuuint32_t(p->ty + 2), 1 };      // starts at x0 - 2: even coordinate
         ok = ok && make_map(&p->mapS[0], S0, 3, dims, str, box) && make_map(&p->mapS[1], S1, 3, dims, str, box);
         ok = ok && make_map(&p->mapPc[0], pc0, 3, dims, str, box) && make_map(&p->mapPc[1], pc1, 3, dims, str, box);
+        // per-cell operands of the plane being finished: the tile itself (tx even: 16-byte rows at 16-byte offsets)
+        cuuint32_t tile[3] = { cuuint32_t(p->tx), cuuint32_t(p->ty), 1 };
+        ok = ok && make_map(&p->mapA, acc_irr, 3, dims, str, tile) && make_map(&p->mapV, inv_porevol, 3, dims, str, tile);
     }
     {
         // the three axis planes of q, G and T: [3][nz][ny][nx] doubles, boxes of (tx+2) x (ty+1) (x boxes start at x0 - 2)
@@ -1270,10 +1277,8 @@ static int launch_box(EuBoxPlan* p, const EuGridDev& g, const EuTablesDev& t, co
     if (p->n_units == 0) return 0;
     lay.b.units = p->d_units;
     lay.b.n_units = p->n_units;
-    lay.b.cmask = p->cmask;
     lay.b.n_flagged = p->n_flagged;
     lay.b.unit_start = p->d_unit_start;
-    lay.b.acc_irr = p->acc_irr;
     int launches = 1;
     // EU_PDL (tuning knob, default 0): programmatic dependent launch -- a kernel's blocks may take their SM slots and run
     // their prologue (rock tables to shared memory, mbarrier set-up) while the previous kernel of the stream drains;
@@ -1305,7 +1310,7 @@ static int launch_box(EuBoxPlan* p, const EuGridDev& g, const EuTablesDev& t, co
     cfg.gridDim = dim3(p->n_blocks);
     cfg.blockDim = dim3(p->threads);
     cfg.dynamicSmemBytes = lay.total;
-    if (cudaLaunchKernelEx(&cfg, kern, p->mapS[cur], p->mapPc[cur], p->mapQ, p->mapG, p->mapT, g, t, f, a, halo, lay.b, slice_lo, slice_hi, (int)tab_bytes) != cudaSuccess) return -1;
+    if (cudaLaunchKernelEx(&cfg, kern, p->mapS[cur], p->mapPc[cur], p->mapQ, p->mapG, p->mapT, p->mapA, p->mapV, g, t, f, a, halo, lay.b, slice_lo, slice_hi, (int)tab_bytes) != cudaSuccess) return -1;
     return launches;
 }
 

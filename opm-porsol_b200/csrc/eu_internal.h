@@ -235,7 +235,8 @@ size_t eu_fast_smem_bytes(const EuTablesDev& t);
 // box kernel (eu_tile.cuh): plane sweep over tiles with TMA-staged operands, for local numberings that are a box
 struct EuBoxPlan;
 EuBoxPlan* eu_box_plan_create(int nx, int ny, int nz, int z_lo, int z_hi, double* S0, double* S1, double* pc0, double* pc1,
-                              double* qa, double* Ga, double* T, const unsigned short* cmask, const int* irr_cells, int n_irr, double* acc_irr, int n_sms);
+                              double* qa, double* Ga, double* T, const unsigned short* cmask, const int* irr_cells, int n_irr, double* acc_irr,
+                              double* inv_porevol, int n_sms);
 void eu_box_plan_destroy(EuBoxPlan* p);
 void eu_box_plan_set_gravity_mask(EuBoxPlan* p, int mask);    // bit a: axis plane a has a non-zero G somewhere
 void eu_box_plan_info(const EuBoxPlan* p, int out[6]);      // tile x, tile y, units, boundary units A, B, threads per block

@@ -37,13 +37,12 @@ struct EuBoxDev {
     int off_bar, off_lam, off_rk, off_stage;      // byte offsets in dynamic shared memory (from the 128-aligned base)
     int lam_bytes, rk_bytes, stage_bytes;
     int off_S, off_pc, off_q, off_G, off_T;       // inside a stage
+    int off_A, off_V, A_bytes;                    // inside a stage: tx x ty boxes of acc_irr and 1 / pore volume of plane k
     int g_mask;                                   // bit a: the faces of axis plane a have a gravity component somewhere (G box loaded)
     int off_fx, off_fy, fx_bytes, fy_bytes;       // SHARE: two buffers each of x+ fluxes [ty][tx+1] and y+ fluxes [ty+1][tx]
     int T_bytes;                                  // one axis' box of q, G or T
     int n_flagged;                // units with a push flag
     const int* unit_start;        // [blocks + 1] block i sweeps units[unit_start[i] .. unit_start[i+1]), flagged ones first
-    const unsigned short* cmask;  // per cell: record slots with faces outside the axis planes
-    const double* acc_irr;        // per cell with a non-zero mask: sum of those faces' contributions (k_box_irregular)
 };
 
 namespace {
@@ -192,7 +191,8 @@ template <bool ROCKS, bool MULTIROCK, bool CAP, int NS, int MINB, bool SHARE>
 __global__ void __launch_bounds__(256, MINB)
 k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUtensorMap mapPc,
            const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapG,
-           const __grid_constant__ CUtensorMap mapT,
+           const __grid_constant__ CUtensorMap mapT, const __grid_constant__ CUtensorMap mapA,
+           const __grid_constant__ CUtensorMap mapV,
            EuGridDev g, EuTablesDev t, EuFastDev f, EuStepArgs a, EuHaloDev halo, EuBoxDev b, int slice_lo, int slice_hi, int tab_bytes)
 {
     TabLayout L;
@@ -237,9 +237,10 @@ k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUt
     const int o_rk = (ly + 1)*txp + lx + 1, o_rk_h = (hy + 1)*txp + hx + 1;
     const int o_S = ((ly + 1)*txs + lx + 2)*8, o_S_h = ((hy + 1)*txs + hx + 2)*8;
     const int o_T = (ly*txp + lx)*8;
+    const int o_A = (ly*tx + lx)*8;
     const int D = b.nx*b.ny;
     const int n_G = __popc(unsigned(b.g_mask) & 7u);
-    const unsigned bundle_bytes = unsigned(txs*(ty + 2)*8*(CAP ? 2 : 1) + (3 + n_G + (CAP ? 3 : 0))*txp*(ty + 1)*8);
+    const unsigned bundle_bytes = unsigned(txs*(ty + 2)*8*(CAP ? 2 : 1) + (3 + n_G + (CAP ? 3 : 0))*txp*(ty + 1)*8 + 2*tx*ty*8);
     const bool hgx = b.g_mask & 1, hgy = b.g_mask & 2, hgz = b.g_mask & 4;        // axis has gravity: its G box is loaded
     const int oGx = b.off_G, oGy = b.off_G + (hgx ? b.T_bytes : 0), oGz = oGy + (hgy ? b.T_bytes : 0);     // G boxes present are packed
     const unsigned char* const stage0 = base + b.off_stage;
@@ -287,6 +288,8 @@ k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUt
             tma_load_4d(st + b.off_T + b.T_bytes, &mapT, x0, y0 - 1, k, 1, bar);
             tma_load_4d(st + b.off_T + 2*b.T_bytes, &mapT, x0, y0, k, 2, bar);
         }
+        tma_load_3d(st + b.off_A, &mapA, x0, y0, k, bar);
+        tma_load_3d(st + b.off_V, &mapV, x0, y0, k, bar);
         P->slot = (ps + 1 == NS) ? 0 : ps + 1;
         if (k + 1 >= un.z) {                                    // on to the block's next unit
             ++pu;
@@ -337,7 +340,6 @@ k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUt
             h_ok = qx >= 0 && qx < b.nx && qy >= 0 && qy < b.ny;
             hc = qx + b.nx*qy + (z0 - 1)*D;
         }
-        unsigned mk = 0u;                                       // mask of the faces outside the axis planes, plane k (none for z0-1)
         int rock_n = 0, rock_hn = 0;                            // rock ids of plane k+1: own cell, halo cell
         if (MULTIROCK && z0 < b.nz) {
             if (active) rock_n = __ldg(f.rock8 + c + D);
@@ -375,20 +377,10 @@ k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUt
             }
         };
         for (int k = z0 - 1; k < z1; ++k) {
-            // operands of plane k that are not staged: requested now, used after the barrier
-            double inv_pv = 0.0;
+            // the one operand of plane k that is not staged: requested now, used after the barrier
             const bool update = active && k >= z0;
             double pcs = 1.0;
-            if (update) {
-                inv_pv = ldg_f64(f.inv_porevol + c);
-                if (CAP && ROCKS) pcs = ldg_f64(f.pcscale + c);
-            }
-            // faces outside the axis planes were summed per cell by k_box_irregular before this launch; the mask of a
-            // plane is fetched one step ahead so that the load of the sum need not wait for it
-            const unsigned mask = mk;
-            double acc_irr = 0.0;
-            if (mask) acc_irr = ldg_f64(b.acc_irr + c);
-            mk = (active && k + 1 < z1) ? unsigned(__ldg(b.cmask + c + D)) : 0u;
+            if (CAP && ROCKS && update) pcs = ldg_f64(f.pcscale + c);
             // rock ids of plane k+1 were requested a step ago; those of plane k+2 are requested now
             const int rock1 = rock_n, rock_h = rock_hn;
             if (MULTIROCK) {
@@ -398,6 +390,11 @@ k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUt
             }
             const unsigned char* st = stage0 + slot*b.stage_bytes;
             mbar_wait(base_u32 + b.off_bar + 8*slot, par);
+            // (per-cell operands of plane k staged with the bundle, read in phase B: 1 / pore volume, and the sum of the
+            // faces outside the axis planes -- k_box_irregular wrote it before this launch; zero for every other cell.
+            // They used to be per-thread loads behind a per-cell mask fetched a plane ahead: the compiler turned the fresh
+            // mask into the next step's predicate right behind the barrier and waited there for the load, 14 % of the
+            // stall samples)
             // ---- phase A: rock curves of plane k+1, once per cell
             unsigned char* ring_next = ring0 + r_next*b.lam_bytes;
             double S1 = 0.0, pc1 = 0.0, lw1 = 0.0, lo1 = 0.0;
@@ -462,8 +459,8 @@ k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUt
                         const double dSy = box_face<ROCKS, MULTIROCK, CAP, true>(L, t, m, ey.x, ey.y, sy.x, sy.y, ryp, qyp, Gyp, hgy, Typ);
                         *reinterpret_cast<double*>(fxw + (ly*txf + lx + 1)*8) = dSx;
                         *reinterpret_cast<double*>(fyw + ((ly + 1)*tx + lx)*8) = dSy;
-                        p_acc = ((m.dS4 - dS5) - dSx) - dSy + acc_irr;
-                        p_S0 = m.S0; p_ipv = inv_pv; p_pcs = pcs; p_lw = m.lw0; p_lo = m.lo0; p_rock = m.rock0;
+                        p_acc = ((m.dS4 - dS5) - dSx) - dSy + *reinterpret_cast<const double*>(st + b.off_A + o_A);
+                        p_S0 = m.S0; p_ipv = *reinterpret_cast<const double*>(st + b.off_V + o_A); p_pcs = pcs; p_lw = m.lw0; p_lo = m.lo0; p_rock = m.rock0;
                     }
                     p_update = update;
                     m.dS4 = dS5;
@@ -533,7 +530,8 @@ k_box_step(const __grid_constant__ CUtensorMap mapS, const __grid_constant__ CUt
                         if (q & 1) acc -= box_face<ROCKS, MULTIROCK, CAP, true>(L, t, m, e.x, e.y, e2.x, e2.y, rq, qq, Gq, gq, Tq);
                         else       acc += box_face<ROCKS, MULTIROCK, CAP, false>(L, t, m, e.x, e.y, e2.x, e2.y, rq, qq, Gq, gq, Tq);
                     }
-                    acc += acc_irr;
+                    acc += *reinterpret_cast<const double*>(st + b.off_A + o_A);
+                    const double inv_pv = *reinterpret_cast<const double*>(st + b.off_V + o_A);
                     OwnMob<false> own0;
                     own0.lw[0] = m.lw0; own0.lo[0] = m.lo0;
                     double pcn;
