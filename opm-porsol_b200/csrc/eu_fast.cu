@@ -933,6 +933,7 @@ struct EuBoxPlan {
     int g_mask = 7;                                  // axis planes with a gravity component (set after the contraction)
     int4* d_units = nullptr;
     int* d_unit_start = nullptr;                    // [n_blocks + 1] unit range of each block
+    int four_blocks = -1;                           // without the capillary term: 1 = two stages, four blocks per SM (-1: not yet known)
     int n_units = 0, n_blocks = 0, n_bnd_units[2] = { 0, 0 }, n_flagged = 0;
     int units_key[5] = { -1, -1, -1, -1, -1 };      // (bnd planes lo, hi, grid blocks, lz override, cap) the unit list was built for
     const unsigned short* cmask = nullptr;
@@ -1237,13 +1238,26 @@ static int launch_box(EuBoxPlan* p, const EuGridDev& g, const EuTablesDev& t, co
     // as many bundles in flight (2..4) as still leave the kernel's resident blocks per SM (3, or 2 with the capillary term)
     static int minb_pre = -1;
     if (minb_pre < 0) { const char* e = getenv("EU_BOX_MINB"); minb_pre = e ? atoi(e) : 0; }
-    const int want_blocks = minb_pre ? minb_pre : (CAP ? 2 : 3);
+    int want_blocks = minb_pre ? minb_pre : (CAP ? 2 : 3);
     int stages = stages_env ? stages_env : 3;
+    if (p->g_mask_seen != p->g_mask) { std::memset(p->smem_set, 0, sizeof(p->smem_set)); std::memset(p->blocks_per_sm, 0, sizeof(p->blocks_per_sm)); p->g_mask_seen = p->g_mask; p->units_key[0] = -1; p->four_blocks = -1; }
     // EU_BOX_SHARE (tuning knob): lateral faces evaluated once per tile and exchanged through shared memory; default: with
     // the capillary term
     static int share_env = -1;
     if (share_env < 0) { const char* e = getenv("EU_BOX_SHARE"); share_env = e ? (atoi(e) != 0 ? 1 : 0) : 2; }
     const bool share = CAP && (share_env == 2 ? true : share_env == 1);
+    if (!CAP && !minb_pre && !stages_env) {
+        // without the capillary term the kernel needs 64 registers (no or one rock table): FOUR blocks per SM are resident
+        // if their shared memory fits, which it does with two stages -- measured 6 % faster than three blocks with three
+        // stages (profiles/README.md, r04d)
+        if (p->four_blocks < 0) {
+            cudaFuncAttributes fa;
+            const BoxLayout l2 = box_layout(*p, CAP, MULTIROCK, 2, tab_bytes, share);
+            p->four_blocks = (cudaFuncGetAttributes(&fa, k_box_step<ROCKS, MULTIROCK, CAP, 2, 3, false>) == cudaSuccess &&
+                              fa.numRegs*p->threads*4 <= 65536 && l2.total <= size_t(227*1024)/4 - 1024) ? 1 : 0;
+        }
+        if (p->four_blocks == 1) want_blocks = 4;
+    }
     BoxLayout lay = box_layout(*p, CAP, MULTIROCK, stages, tab_bytes, share);
     const size_t budget = size_t(227*1024)/want_blocks - 1024;
     while (!stages_env && stages > 2 && lay.total > budget) lay = box_layout(*p, CAP, MULTIROCK, --stages, tab_bytes, share);
@@ -1259,7 +1273,6 @@ static int launch_box(EuBoxPlan* p, const EuGridDev& g, const EuTablesDev& t, co
     // function attributes are per device: a plan remembers what it set on ITS device (several solvers, one per GPU, may
     // live in one process)
     const int vkey = (share ? 16 : 0) + (minb_env == 4 ? 8 : 0) + (two ? 4 : 0) + stages - 2;
-    if (p->g_mask_seen != p->g_mask) { std::memset(p->smem_set, 0, sizeof(p->smem_set)); std::memset(p->blocks_per_sm, 0, sizeof(p->blocks_per_sm)); p->g_mask_seen = p->g_mask; p->units_key[0] = -1; }
     if (lay.total > p->smem_set[vkey]) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.total) != cudaSuccess) return -1;
         p->smem_set[vkey] = lay.total;
