@@ -313,6 +313,15 @@ int eu_post_process_fluxes(int n_cells, const int* hf_offset, const int* hf_neig
                            const int* partner_face, double* hf_flux, double* max_modification);
 int eu_write_field(const double* field, long long n, const char* filename);
 
+/* Test hook (no device needed): the work units of the box kernel's sweep for a grid of nx x ny cells per plane, tiles of
+ * tx x ty, own planes [z_lo, z_hi), bnd_lo / bnd_hi boundary planes whose cells a neighbour rank keeps as ghosts, and
+ * grid_blocks resident blocks; spans != 0 asks for the equal-span partition (EU_BOX_UNITS=spans), lz > 0 fixes the chunk
+ * length.  units4[4 i ..] = {x0 | y0 << 16, first plane, last plane + 1, flags (bit 0 / 1: pushes to the rank below /
+ * above)} block after block, start[0 .. *n_blocks] the blocks' ranges.  Returns the number of units, -1 on bad arguments
+ * (or a too small buffer).  No reference counterpart: the reference walks cells in a serial loop. */
+int eu_debug_box_units(int nx, int ny, int tx, int ty, int z_lo, int z_hi, int bnd_lo, int bnd_hi, int grid_blocks,
+                       int spans, int lz, int* units4, int max_units, int* start, int max_start, int* n_blocks);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,6 +14,7 @@
 // Per cell the kernel first loads all its records, then issues every gather (neighbour S, pc, face q/G/T)
 // before any arithmetic, so a warp has 6-8 independent loads per lane in flight instead of a chain.
 #include "eu_internal.h"
+#include "eu_box_units.h"
 
 #include <algorithm>
 #include <cstdio>
@@ -1091,118 +1092,29 @@ void eu_box_plan_info(const EuBoxPlan* p, int out[6])
     out[0] = p->tx; out[1] = p->ty; out[2] = p->n_units; out[3] = p->n_bnd_units[0]; out[4] = p->n_bnd_units[1]; out[5] = p->threads;
 }
 
-// Work units: tiles x z-chunks of the own planes.  With a neighbour rank below / above, the chunks that contain the
-// bnd_lo / bnd_hi planes whose cells the neighbour keeps as ghosts are flagged (bit 0 / bit 1) and come first in the list:
-// the kernel pushes those cells' results to the neighbour as it sweeps them and counts the finished flagged units; the
-// neighbour needs the flag only when its next substep starts, a whole kernel later.  The chunk length balances
-// (units per block) x (planes + 1 prologue step per unit).
-static int box_chunks(const EuBoxPlan* p, int grid_blocks, int lz_env, int min_len)
-{
-    const int tiles = ((p->nx + p->tx - 1)/p->tx)*((p->ny + p->ty - 1)/p->ty);
-    const int planes = p->z_hi - p->z_lo;
-    int best_chunks = 1;
-    double best = 1e300;
-    for (int chunks = 1; chunks <= planes; ++chunks) {
-        const double len = double(planes)/chunks;
-        if (len < std::max(min_len, 1) && chunks > 1) break;
-        if (lz_env > 0) { if (len <= lz_env || chunks == planes) { best_chunks = chunks; break; } continue; }
-        if (len > 64.0) continue;
-        const double rounds = double(((long long)chunks*tiles + grid_blocks - 1)/grid_blocks);
-        const double cost = rounds*(len + 1.3);
-        if (cost < best - 1e-9) { best = cost; best_chunks = chunks; }
-    }
-    return best_chunks;
-}
-
-// EU_BOX_UNITS (tuning knob, read at every plan build): "chunks" (default) or "spans".
-//   chunks  every tile's planes cut into the same number of z-chunks (box_chunks), handed out round-robin.  A block may
-//           do one unit more than another, but the blocks of one SM share its issue slots, so what counts is the sum
-//           per SM, and that differs by one unit in ~40
-//   spans   the (tile, plane) pairs in tile-major order cut into one span of equal length per block; a span is split into
-//           units at tile boundaries, and a cut closer than min_piece planes to a tile boundary moves onto it (so the
-//           planes next to a slab boundary stay in ONE unit per tile, as the unit counters of the exchange assume).
-//           Measured (profiles/README.md, r04a): 512x512x256 2.6 % slower than chunks (neighbouring tiles are no longer
-//           swept at the same time: less halo reuse in L2), 32-plane slab 1.5 % faster, C3 0.7 % faster
-static int box_units_mode()
-{
-    const char* e = getenv("EU_BOX_UNITS");
-    return (e && std::strcmp(e, "spans") == 0) ? 1 : 0;
-}
-
+// Work units of the sweep: the host logic is eu_box_make_units (eu_host.cpp; tested without a device through
+// eu_debug_box_units).  EU_BOX_UNITS=spans / EU_BOX_LZ=<planes> (tuning knobs, read at every plan build) choose the other
+// partition / a fixed chunk length.
 static int box_build_units(EuBoxPlan* p, int bnd_lo, int bnd_hi, int grid_blocks, bool cap)
 {
     const char* e = getenv("EU_BOX_LZ");
     const int lz_env = e ? atoi(e) : 0;
-    const int mode = box_units_mode();
+    const char* eu = getenv("EU_BOX_UNITS");
+    const int mode = (eu && std::strcmp(eu, "spans") == 0) ? 1 : 0;
     const int lz_key = lz_env + 100000*mode;
     if (p->units_key[0] == bnd_lo && p->units_key[1] == bnd_hi && p->units_key[2] == grid_blocks && p->units_key[3] == lz_key &&
         p->units_key[4] == int(cap) && p->d_units) return 0;
-    const int tiles_x = (p->nx + p->tx - 1)/p->tx, tiles_y = (p->ny + p->ty - 1)/p->ty, tiles = tiles_x*tiles_y;
-    const int planes = p->z_hi - p->z_lo;
-    std::vector<int4> units;            // block after block, a block's flagged units first
+    static_assert(sizeof(EuBoxUnit) == sizeof(int4), "unit records are uploaded as int4");
+    std::vector<EuBoxUnit> units;       // block after block, a block's flagged units first
     std::vector<int> start;             // [blocks + 1]
-    auto unit_of = [&](int tile, int s, int e2) {
-        const int txi = tile % tiles_x, tyi = tile/tiles_x;
-        const int flags = ((bnd_lo > 0 && s == 0) ? 1 : 0) | ((bnd_hi > 0 && e2 == planes) ? 2 : 0);
-        return make_int4((txi*p->tx) | ((tyi*p->ty) << 16), p->z_lo + s, p->z_lo + e2, flags);
-    };
-    if (tiles > 0 && planes > 0 && (mode == 0 || lz_env > 0 || bnd_lo > 0 || bnd_hi > 0)) {        // (spans: single-rank runs only)
-        const int chunks = box_chunks(p, grid_blocks, lz_env, std::max(bnd_lo, bnd_hi));
-        std::vector<int4> flat;
-        auto add = [&](int q) {
-            const int s = int((long long)planes*q/chunks), e2 = int((long long)planes*(q + 1)/chunks);
-            if (e2 <= s) return;
-            for (int tile = 0; tile < tiles; ++tile) flat.push_back(unit_of(tile, s, e2));
-        };
-        // flagged chunks first
-        if (bnd_lo > 0) add(0);
-        if (bnd_hi > 0 && (chunks > 1 || bnd_lo == 0)) add(chunks - 1);
-        for (int q = 0; q < chunks; ++q) {
-            if ((bnd_lo > 0 && q == 0) || (bnd_hi > 0 && q == chunks - 1)) continue;
-            add(q);
-        }
-        const int blocks = std::max(1, std::min(grid_blocks, int(flat.size())));
-        for (int i = 0; i < blocks; ++i) {
-            start.push_back(int(units.size()));
-            for (size_t u = size_t(i); u < flat.size(); u += size_t(blocks)) units.push_back(flat[u]);
-        }
-        start.push_back(int(units.size()));
-    } else if (tiles > 0 && planes > 0) {
-        const long long W = (long long)tiles*planes;
-        const int min_piece = std::max(std::max(bnd_lo, bnd_hi), 3);
-        const int blocks = int(std::max(1LL, std::min((long long)grid_blocks, W/4)));
-        std::vector<long long> cut(size_t(blocks) + 1);
-        for (int i = 0; i <= blocks; ++i) {
-            const long long pos = W*i/blocks;
-            long long tile = pos/planes;
-            int s = int(pos % planes);
-            if (s < min_piece) s = 0;
-            else if (s > planes - min_piece) { s = 0; ++tile; }
-            cut[size_t(i)] = tile*planes + s;
-        }
-        cut[0] = 0; cut[size_t(blocks)] = W;
-        for (int i = 0; i < blocks; ++i) {
-            start.push_back(int(units.size()));
-            const size_t first = units.size();
-            for (long long pos = cut[size_t(i)]; pos < cut[size_t(i) + 1]; ) {
-                const int tile = int(pos/planes), s = int(pos % planes);
-                const int e2 = int(std::min((long long)planes, s + (cut[size_t(i) + 1] - pos)));
-                units.push_back(unit_of(tile, s, e2));
-                pos += e2 - s;
-            }
-            std::stable_partition(units.begin() + first, units.end(), [](const int4& un) { return un.w != 0; });
-        }
-        start.push_back(int(units.size()));
-    }
+    if (eu_box_make_units(p->nx, p->ny, p->tx, p->ty, p->z_lo, p->z_hi, bnd_lo, bnd_hi, grid_blocks, mode, lz_env, units, start) < 0) return -1;
     p->n_bnd_units[0] = p->n_bnd_units[1] = 0;
     p->n_flagged = 0;
-    for (const int4& un : units) {
-        if (un.w) ++p->n_flagged;
-        if (un.w & 1) ++p->n_bnd_units[0];
-        if (un.w & 2) ++p->n_bnd_units[1];
+    for (const EuBoxUnit& un : units) {
+        if (un.flags) ++p->n_flagged;
+        if (un.flags & 1) ++p->n_bnd_units[0];
+        if (un.flags & 2) ++p->n_bnd_units[1];
     }
-    // the exchange counts ONE finished unit per tile and boundary (eu_box_plan_units)
-    if ((bnd_lo > 0 && p->n_bnd_units[0] != tiles) || (bnd_hi > 0 && p->n_bnd_units[1] != tiles)) return -1;
     if (p->d_units) { cudaFree(p->d_units); p->d_units = nullptr; }
     if (p->d_unit_start) { cudaFree(p->d_unit_start); p->d_unit_start = nullptr; }
     p->n_units = int(units.size());

@@ -5,6 +5,7 @@
 // not hold the reference's property class (bench.py, the Python binding).  The drop-in C++ header
 // does not use it: it asks the caller's ReservoirProperties object for cflFactor*() directly.
 #include "../../include/euler_b200.h"
+#include "eu_box_units.h"
 
 #include <algorithm>
 #include <cmath>
@@ -298,3 +299,132 @@ int eu_write_field(const double* field, long long n, const char* filename)
 }
 
 } // extern "C"
+
+
+// ---- work units of the box kernel (host logic of eu_tile.cuh's sweep; no device needed) -------------------------------
+//
+// Work units: tiles x z-ranges of the own planes [z_lo, z_hi), listed block after block (block i sweeps
+// units[start[i] .. start[i+1]), in that order).  With a neighbour rank below / above, the unit of a tile that contains
+// the bnd_lo / bnd_hi planes whose cells the neighbour keeps as ghosts is flagged (bit 0 / bit 1) and comes first in its
+// block's list: the kernel pushes those cells' results to the neighbour as it sweeps them and counts the finished flagged
+// units -- ONE per tile and boundary, which is what the exchange's counters are set to (eu_box_plan_units).
+//
+//   chunks (spans == 0)  every tile's planes cut into the same number of z-chunks, handed out round-robin.  The chunk
+//           length balances (units per block) x (planes + 1 prologue step per unit); lz > 0 fixes the length.  A block
+//           may do one unit more than another, but the blocks of one SM share its issue slots, so what counts is the sum
+//           per SM, and that differs by one unit in ~40
+//   spans   the (tile, plane) pairs in tile-major order cut into one span of equal length per block; a span is split into
+//           units at tile boundaries, and a cut closer than min_piece planes to a tile boundary moves onto it (so the
+//           planes next to a slab boundary stay in ONE unit per tile).  Single-rank runs only.
+//           Measured (profiles/README.md, r04a): 512x512x256 2.6 % slower than chunks (neighbouring tiles are no longer
+//           swept at the same time: less halo reuse in L2), 32-plane slab 1.5 % faster, C3 0.7 % faster
+namespace {
+
+int box_chunks(int tiles, int planes, int grid_blocks, int lz, int min_len)
+{
+    int best_chunks = 1;
+    double best = 1e300;
+    for (int chunks = 1; chunks <= planes; ++chunks) {
+        const double len = double(planes)/chunks;
+        if (len < std::max(min_len, 1) && chunks > 1) break;
+        if (lz > 0) { if (len <= lz || chunks == planes) { best_chunks = chunks; break; } continue; }
+        if (len > 64.0) continue;
+        const double rounds = double(((long long)chunks*tiles + grid_blocks - 1)/grid_blocks);
+        const double cost = rounds*(len + 1.3);
+        if (cost < best - 1e-9) { best = cost; best_chunks = chunks; }
+    }
+    return best_chunks;
+}
+
+} // namespace
+
+int eu_box_make_units(int nx, int ny, int tx, int ty, int z_lo, int z_hi, int bnd_lo, int bnd_hi, int grid_blocks, int spans,
+                      int lz, std::vector<EuBoxUnit>& units, std::vector<int>& start)
+{
+    units.clear();
+    start.clear();
+    if (nx < 1 || ny < 1 || tx < 1 || ty < 1 || grid_blocks < 1 || bnd_lo < 0 || bnd_hi < 0) return -1;
+    const int tiles_x = (nx + tx - 1)/tx, tiles_y = (ny + ty - 1)/ty, tiles = tiles_x*tiles_y;
+    const int planes = z_hi - z_lo;
+    if (planes <= 0) return 0;
+    if (std::max(bnd_lo, bnd_hi) > planes) return -1;
+    auto unit_of = [&](int tile, int s, int e2) {
+        const int txi = tile % tiles_x, tyi = tile/tiles_x;
+        EuBoxUnit un;
+        un.xy = (txi*tx) | ((tyi*ty) << 16);
+        un.z0 = z_lo + s;
+        un.z1 = z_lo + e2;
+        un.flags = ((bnd_lo > 0 && s == 0) ? 1 : 0) | ((bnd_hi > 0 && e2 == planes) ? 2 : 0);
+        return un;
+    };
+    if (!spans || lz > 0 || bnd_lo > 0 || bnd_hi > 0) {
+        const int chunks = box_chunks(tiles, planes, grid_blocks, lz, std::max(bnd_lo, bnd_hi));
+        std::vector<EuBoxUnit> flat;
+        auto add = [&](int q) {
+            const int s = int((long long)planes*q/chunks), e2 = int((long long)planes*(q + 1)/chunks);
+            if (e2 <= s) return;
+            for (int tile = 0; tile < tiles; ++tile) flat.push_back(unit_of(tile, s, e2));
+        };
+        // flagged chunks first
+        if (bnd_lo > 0) add(0);
+        if (bnd_hi > 0 && (chunks > 1 || bnd_lo == 0)) add(chunks - 1);
+        for (int q = 0; q < chunks; ++q) {
+            if ((bnd_lo > 0 && q == 0) || (bnd_hi > 0 && q == chunks - 1)) continue;
+            add(q);
+        }
+        const int blocks = std::max(1, std::min(grid_blocks, int(flat.size())));
+        for (int i = 0; i < blocks; ++i) {
+            start.push_back(int(units.size()));
+            for (size_t u = size_t(i); u < flat.size(); u += size_t(blocks)) units.push_back(flat[u]);
+        }
+        start.push_back(int(units.size()));
+    } else {
+        const long long W = (long long)tiles*planes;
+        const int min_piece = 3;
+        const int blocks = int(std::max(1LL, std::min((long long)grid_blocks, W/4)));
+        std::vector<long long> cut(size_t(blocks) + 1);
+        for (int i = 0; i <= blocks; ++i) {
+            const long long pos = W*i/blocks;
+            long long tile = pos/planes;
+            int s = int(pos % planes);
+            if (s < min_piece) s = 0;
+            else if (s > planes - min_piece) { s = 0; ++tile; }
+            cut[size_t(i)] = tile*planes + s;
+        }
+        cut[0] = 0; cut[size_t(blocks)] = W;
+        for (int i = 0; i < blocks; ++i) {
+            start.push_back(int(units.size()));
+            for (long long pos = cut[size_t(i)]; pos < cut[size_t(i) + 1]; ) {
+                const int tile = int(pos/planes), s = int(pos % planes);
+                const int e2 = int(std::min((long long)planes, s + (cut[size_t(i) + 1] - pos)));
+                units.push_back(unit_of(tile, s, e2));
+                pos += e2 - s;
+            }
+        }
+        start.push_back(int(units.size()));
+    }
+    // the exchange counts ONE finished unit per tile and boundary
+    int n0 = 0, n1 = 0;
+    for (const EuBoxUnit& un : units) { if (un.flags & 1) ++n0; if (un.flags & 2) ++n1; }
+    if ((bnd_lo > 0 && n0 != tiles) || (bnd_hi > 0 && n1 != tiles)) return -1;
+    return int(units.size());
+}
+
+extern "C" int eu_debug_box_units(int nx, int ny, int tx, int ty, int z_lo, int z_hi, int bnd_lo, int bnd_hi, int grid_blocks,
+                                  int spans, int lz, int* units4, int max_units, int* start, int max_start, int* n_blocks)
+{
+    std::vector<EuBoxUnit> u;
+    std::vector<int> st;
+    const int n = eu_box_make_units(nx, ny, tx, ty, z_lo, z_hi, bnd_lo, bnd_hi, grid_blocks, spans, lz, u, st);
+    if (n < 0) return -1;
+    if (n_blocks) *n_blocks = st.empty() ? 0 : int(st.size()) - 1;
+    if (units4) {
+        if (n > max_units) return -1;
+        for (int i = 0; i < n; ++i) { units4[4*i] = u[size_t(i)].xy; units4[4*i + 1] = u[size_t(i)].z0; units4[4*i + 2] = u[size_t(i)].z1; units4[4*i + 3] = u[size_t(i)].flags; }
+    }
+    if (start) {
+        if (int(st.size()) > max_start) return -1;
+        std::copy(st.begin(), st.end(), start);
+    }
+    return n;
+}
